@@ -1,0 +1,114 @@
+/* mplu.h -- thin C ABI of the B200-native mixed-precision LU + iterative-refinement solver.
+ *
+ * The reference (Keyteer/Mixed-precision_LU_Factorization) exposes exactly one host entry point,
+ *     void MPF(double *h_A, int N, int r, int *IPIV);            -- /root/reference/MPF.h:3, MPF.cu:66-256
+ * with C++ linkage, no status and no solve path.  That symbol is kept byte-compatible in include/MPF.h.  This header
+ * is the C-ABI layer BASELINE.json's north_star asks for on top of it: plain pointers and sizes, explicit status
+ * codes, device-resident and host-buffer variants of factor / solve / gesv.  Every function returns 0 on success,
+ * a positive cudaError_t value for CUDA failures, or a negative MPLU_E_* code.
+ *
+ * Layout conventions are the reference's: matrices are column-major (benchmark.cpp:19 prints mat[j*n+i]), leading
+ * dimension in elements, fp64 on the interface.
+ */
+#ifndef MPLU_H
+#define MPLU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mplu_context mplu_context;
+
+enum {
+    MPLU_OK = 0,
+    MPLU_E_ARG = -1,        /* bad argument */
+    MPLU_E_NODEVICE = -2,   /* no CUDA device (the reference prints and returns: MPF.cu:72-75) */
+    MPLU_E_NOTFACTORED = -3,
+    MPLU_E_TMAP = -4,       /* TMA descriptor encoding failed */
+    MPLU_E_OVERFLOW = -5,   /* a 16-bit panel value left the fp16 range (factorization unusable) */
+    MPLU_E_ZEROPIVOT = -6,  /* exact zero pivot met without pivoting */
+    MPLU_E_NOCONV = -7      /* refinement did not reach the tolerance in max_iters (x holds the last iterate) */
+};
+
+enum { MPLU_FP16 = 0, MPLU_BF16 = 1 };
+enum { MPLU_GEMM_AUTO = -1, MPLU_GEMM_CG1 = 0, MPLU_GEMM_CG2 = 1 };
+
+typedef struct mplu_options {
+    int precision;    /* MPLU_FP16 (default) or MPLU_BF16: panel/operand storage type; accumulation is fp32 */
+    int nb;           /* outer (trailing-update) block size, multiple of 128; default 1024 */
+    int max_iters;    /* refinement iteration cap, default 30 (LAPACK dsgesv ITERMAX) */
+    double tol;       /* <= 0: dsgesv rule ||r||_inf <= ||x||_inf ||A||_inf eps sqrt(n); else relative to ||A|| ||x|| */
+    int gemm_variant; /* MPLU_GEMM_AUTO / CG1 (128x256 tiles) / CG2 (CTA-pair 256x256 tiles) */
+    int max_sms;      /* 0 = all SMs */
+    int a_exp;        /* fp16 only: A-type shadows are scaled so max|A| maps into (2^(a_exp-1), 2^a_exp]; default 11 */
+    int l_exp;        /* fp16 only: multipliers are scaled by 2^l_exp; default 11 */
+} mplu_options;
+
+typedef struct mplu_stats {
+    int n;
+    int iters;              /* refinement (correction) solves performed */
+    int converged;          /* 1 if the stopping rule was met */
+    int status_bits;        /* bit0 fp16 overflow, bit1 zero pivot, bit2 non-finite inverse */
+    double anorm_inf;       /* ||A||_inf */
+    double bnorm_inf;       /* ||b||_inf */
+    double xnorm_inf;       /* ||x||_inf */
+    double rnorm_inf;       /* ||b - A x||_inf, fp64 */
+    double backward_error;  /* rnorm / (anorm*xnorm + bnorm) */
+    double first_backward_error; /* same quantity after the un-refined first solve */
+    float factor_ms;        /* device time of the factorization (CUDA events) */
+    float solve_ms;         /* device time of first solve + refinement */
+    float total_ms;         /* factor + solve (+ copies for the host variant) */
+    float h2d_ms, d2h_ms;   /* host variant only */
+    int gemm_launches;      /* tcgen05 GEMM launches in the factorization */
+    int kernel_launches;    /* all kernel launches (factor + solve) */
+} mplu_stats;
+
+void mplu_default_options(mplu_options *opts);
+
+int mplu_create(mplu_context **ctx, int device);
+void mplu_destroy(mplu_context *ctx);
+
+/* Factor the n x n fp64 matrix dA (device memory, column-major, lda) without pivoting: blocked right-looking LU,
+ * fp16/bf16 operands, fp32 accumulation and fp32 factor storage inside the context.  dA is not modified.
+ * Replaces the panel loop of MPF (MPF.cu:100-241) for the no-pivot case. */
+int mplu_factor_device(mplu_context *ctx, int n, const double *dA, long long lda, const mplu_options *opts);
+
+/* Solve A x = b with the stored factors and fp64 iterative refinement against the ORIGINAL dA. */
+int mplu_solve_device(mplu_context *ctx, const double *dA, long long lda, const double *db, double *dx,
+                      mplu_stats *stats);
+
+/* factor + solve, device-resident inputs (the headline metric's timed region). */
+int mplu_gesv_device(mplu_context *ctx, int n, const double *dA, long long lda, const double *db, double *dx,
+                     const mplu_options *opts, mplu_stats *stats);
+
+/* factor + solve from HOST buffers (pageable or pinned): H2D of A and b, D2H of x inside the call. */
+int mplu_gesv_host(mplu_context *ctx, int n, const double *hA, long long lda, const double *hb, double *hx,
+                   const mplu_options *opts, mplu_stats *stats);
+
+/* Copy the fp32 L\U factors (unit-lower L below the diagonal, U on/above: the dgetrf layout MPF returns) widened
+ * to fp64 into a column-major n x n array; `on_device` selects the destination memory space. */
+int mplu_get_factors(mplu_context *ctx, double *LU, long long ldlu, int on_device);
+
+/* The stream all work of this context is enqueued on (a cudaStream_t). */
+void *mplu_stream(mplu_context *ctx);
+
+/* ---- kernel-level entry points (used by the parity tests and by callers that bring their own orchestration) ---- */
+
+/* C(MxN, fp32, col-major) = beta*C + alpha * A(MxK) * B(KxN); A,B 16-bit column-major device arrays.
+ * variant: 0 CG1, 1 CG2 (A column-major), 2/3 same with A passed as its transpose (K x M column-major).
+ * H (optional) receives the 16-bit copy of the result scaled by hscale. */
+int mplu_gemm16(int variant, int bf16, int M, int N, int K, float alpha, const void *dA, long long lda,
+                const void *dB, long long ldb, float beta, float *dC, long long ldc, void *dH, long long ldh,
+                float hscale, int max_sms, void *stream);
+
+/* No-pivot LU of one 128x128 fp32 block in place + explicit inverses (fp32, column-major 128x128 each). */
+int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *stream);
+
+/* r = b - A x in fp64; norms[0] = ||r||_inf, norms[1] = ||x||_inf (device array of 2 doubles). */
+int mplu_residual(int n, const double *dA, long long lda, const double *dx, const double *db, double *dr,
+                  double *dnorms, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPLU_H */

@@ -1,0 +1,199 @@
+"""ctypes binding of libmplu.so -- the B200-native mixed-precision LU + iterative refinement solver.
+
+Python is plumbing only (device memory via torch, tests, bench); every numerical step runs in the CUDA kernels of
+csrc/.  The library must be present: there is no CPU or PyTorch fallback, loading fails loudly instead.
+
+Mirrors the reference's interface for this path: ``MPF(A, N, r, IPIV)`` (/root/reference/MPF.h:3) plus the
+``mplu_*`` C ABI of include/mplu.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libmplu.so"
+
+MPLU_FP16, MPLU_BF16 = 0, 1
+GEMM_AUTO, GEMM_CG1, GEMM_CG2 = -1, 0, 1
+
+ERRORS = {
+    0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "not factored", -4: "TMA descriptor encoding failed",
+    -5: "fp16 overflow in a panel", -6: "zero pivot", -7: "refinement did not converge",
+}
+
+
+class Options(C.Structure):
+    _fields_ = [("precision", C.c_int), ("nb", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double),
+                ("gemm_variant", C.c_int), ("max_sms", C.c_int), ("a_exp", C.c_int), ("l_exp", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n", C.c_int), ("iters", C.c_int), ("converged", C.c_int), ("status_bits", C.c_int),
+                ("anorm_inf", C.c_double), ("bnorm_inf", C.c_double), ("xnorm_inf", C.c_double),
+                ("rnorm_inf", C.c_double), ("backward_error", C.c_double), ("first_backward_error", C.c_double),
+                ("factor_ms", C.c_float), ("solve_ms", C.c_float), ("total_ms", C.c_float),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("gemm_launches", C.c_int),
+                ("kernel_launches", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MpluError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = ERRORS.get(code, f"cudaError {code}" if code > 0 else f"error {code}")
+        super().__init__(f"{where}: {msg} ({code})")
+
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """Load libmplu.so (built by build.py / __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: run `python __graft_entry__.py build` (no CPU fallback exists)")
+    lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    vp, ll, i, f, d = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
+    lib.mplu_default_options.argtypes = [C.POINTER(Options)]
+    lib.mplu_default_options.restype = None
+    lib.mplu_create.argtypes = [C.POINTER(vp), i]
+    lib.mplu_destroy.argtypes = [vp]
+    lib.mplu_destroy.restype = None
+    lib.mplu_stream.argtypes = [vp]
+    lib.mplu_stream.restype = vp
+    lib.mplu_factor_device.argtypes = [vp, i, vp, ll, C.POINTER(Options)]
+    lib.mplu_solve_device.argtypes = [vp, vp, ll, vp, vp, C.POINTER(Stats)]
+    lib.mplu_gesv_device.argtypes = [vp, i, vp, ll, vp, vp, C.POINTER(Options), C.POINTER(Stats)]
+    lib.mplu_gesv_host.argtypes = [vp, i, vp, ll, vp, vp, C.POINTER(Options), C.POINTER(Stats)]
+    lib.mplu_get_factors.argtypes = [vp, vp, ll, i]
+    lib.mplu_gemm16.argtypes = [i, i, i, i, i, f, vp, ll, vp, ll, f, vp, ll, vp, ll, f, i, vp]
+    lib.mplu_diag_lu128.argtypes = [vp, ll, vp, vp, vp]
+    lib.mplu_residual.argtypes = [i, vp, ll, vp, vp, vp, vp, vp]
+    for name in ("mplu_create", "mplu_factor_device", "mplu_solve_device", "mplu_gesv_device", "mplu_gesv_host",
+                 "mplu_get_factors", "mplu_gemm16", "mplu_diag_lu128", "mplu_residual"):
+        getattr(lib, name).restype = i
+    if hasattr(lib, "mplu_MPF"):
+        lib.mplu_MPF.argtypes = [vp, i, i, vp]
+        lib.mplu_MPF.restype = i
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    load_library().mplu_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f"unknown option {k}")
+        setattr(o, k, v)
+    return o
+
+
+def _check(code: int, where: str, allow=()):
+    if code != 0 and code not in allow:
+        raise MpluError(code, where)
+    return code
+
+
+class Solver:
+    """One solver context (one CUDA device, one stream, reusable workspaces)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        _check(self._lib.mplu_create(C.byref(self._ctx), device), "mplu_create")
+
+    def close(self):
+        if self._ctx:
+            self._lib.mplu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return self._lib.mplu_stream(self._ctx) or 0
+
+    # raw device pointers -------------------------------------------------------------------------------------
+    def factor_ptr(self, n, dA, lda, opts=None):
+        _check(self._lib.mplu_factor_device(self._ctx, n, dA, lda, C.byref(opts) if opts else None), "mplu_factor_device")
+
+    def solve_ptr(self, dA, lda, db, dx, allow_noconv=False) -> Stats:
+        st = Stats()
+        _check(self._lib.mplu_solve_device(self._ctx, dA, lda, db, dx, C.byref(st)), "mplu_solve_device",
+               allow=(-7,) if allow_noconv else ())
+        return st
+
+    def gesv_ptr(self, n, dA, lda, db, dx, opts=None, allow_noconv=False) -> Stats:
+        st = Stats()
+        _check(self._lib.mplu_gesv_device(self._ctx, n, dA, lda, db, dx, C.byref(opts) if opts else None, C.byref(st)),
+               "mplu_gesv_device", allow=(-7,) if allow_noconv else ())
+        return st
+
+    def gesv_host_ptr(self, n, hA, lda, hb, hx, opts=None, allow_noconv=False) -> Stats:
+        st = Stats()
+        _check(self._lib.mplu_gesv_host(self._ctx, n, hA, lda, hb, hx, C.byref(opts) if opts else None, C.byref(st)),
+               "mplu_gesv_host", allow=(-7,) if allow_noconv else ())
+        return st
+
+    # torch conveniences (column-major convention: pass A.t().contiguous() storage, i.e. a tensor whose memory is
+    # column-major; helpers below take "colmajor" tensors of shape (n, n) created with torch.empty(n, n).t()) -----
+    def gesv(self, A_cm, b, opts=None, allow_noconv=False):
+        """A_cm: torch fp64 CUDA tensor whose storage is column-major n x n (e.g. M.t() of a contiguous M^T)."""
+        import torch
+        n = A_cm.shape[0]
+        assert A_cm.dtype == torch.float64 and A_cm.is_cuda and A_cm.stride(0) == 1
+        lda = A_cm.stride(1)
+        x = torch.empty(n, dtype=torch.float64, device=A_cm.device)
+        torch.cuda.synchronize(A_cm.device)
+        st = self.gesv_ptr(n, A_cm.data_ptr(), lda, b.data_ptr(), x.data_ptr(), opts, allow_noconv)
+        return x, st
+
+    def factors(self, n):
+        import torch
+        LU = torch.empty(n, n, dtype=torch.float64, device="cuda").t()  # column-major storage
+        _check(self._lib.mplu_get_factors(self._ctx, LU.data_ptr(), n, 1), "mplu_get_factors")
+        return LU
+
+
+def gemm16(variant, A, B, C_io=None, alpha=1.0, beta=0.0, want_shadow=False, hscale=1.0, max_sms=0, a_transposed=None):
+    """Kernel-level hook used by the parity tests.  A (M x K) and B (K x N) are 16-bit CUDA tensors with
+    column-major storage (stride(0) == 1); for variants 2/3 pass `a_transposed` = K x M column-major instead."""
+    import torch
+    lib = load_library()
+    if variant in (2, 3):
+        At = a_transposed
+        K, M = At.shape
+        a_ptr, lda = At.data_ptr(), At.stride(1)
+        dt = At.dtype
+    else:
+        M, K = A.shape
+        assert A.stride(0) == 1
+        a_ptr, lda = A.data_ptr(), A.stride(1)
+        dt = A.dtype
+    K2, N = B.shape
+    assert K2 == K and B.stride(0) == 1
+    bf16 = 1 if dt == torch.bfloat16 else 0
+    if C_io is None:
+        C_io = torch.zeros(N, M, dtype=torch.float32, device=B.device).t()
+    assert C_io.stride(0) == 1
+    H = torch.zeros(N, M, dtype=dt, device=B.device).t() if want_shadow else None
+    torch.cuda.synchronize()
+    rc = lib.mplu_gemm16(variant, bf16, M, N, K, alpha, a_ptr, lda, B.data_ptr(), B.stride(1), beta,
+                         C_io.data_ptr(), C_io.stride(1), H.data_ptr() if H is not None else None,
+                         H.stride(1) if H is not None else 0, hscale, max_sms, None)
+    _check(rc, "mplu_gemm16")
+    torch.cuda.synchronize()
+    return (C_io, H) if want_shadow else C_io

@@ -1,0 +1,58 @@
+// Host-side interface of the tcgen05 trailing-update GEMM (see gemm_tc.cu).
+//
+//   out(m,n) = cin(m,n) + alpha * sum_k A(m,k) * B(k,n)          m < M, n < N, K % 64 == 0
+//
+// A, B are 16-bit (fp16 or bf16) column-major matrices described by TMA tensor maps that cover the WHOLE parent
+// array; the sub-block a GEMM works on is selected with element origins (a_r0,a_c0)/(b_r0,b_c0).  This is the
+// Schur-complement update A22 -= L21*U12 of the reference (cublasDgemm at /root/reference/MPF.cu:230-239) and, with
+// an explicitly inverted triangular block as one operand, its TRSM (cublasDtrsm at MPF.cu:215-225).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mplu {
+
+enum GemmVariant : int {
+    GEMM_CG1_AMN = 0,  // 1-CTA tiles 128x256, A column-major (M contiguous)
+    GEMM_CG2_AMN = 1,  // CTA-pair tiles 256x256, A column-major
+    GEMM_CG1_AK = 2,   // 1-CTA, A given as its transpose: parent array is K x M column-major (K contiguous)
+    GEMM_CG2_AK = 3,   // CTA-pair, same A layout; for these two (a_r0,a_c0) = (k0, m0) in the transposed parent
+};
+
+struct GemmParams {
+    int M, N, K;
+    int a_r0, a_c0;  // origin of the A block inside its parent array: (row m0, col k0)
+    int b_r0, b_c0;  // origin of the B block inside its parent array: (row k0, col n0)
+    float* C;        // fp32 output, column-major, already offset to the block origin (may be null)
+    long long ldc;
+    const float* Cin;  // fp32 addend (may alias C; null = none)
+    long long ldcin;
+    const double* Cin64;  // fp64 addend used instead of Cin on an element's first touch (null = none)
+    long long ldc64;
+    void* H;  // optional 16-bit shadow of the output, column-major, offset to the block origin
+    long long ldh;
+    int h_rows, h_cols;     // shadow is written where (m < h_rows || n < h_cols)
+    float alpha;            // static factor ...
+    const float* alpha_p1;  // ... times *alpha_p1 (device, null = 1)
+    const float* alpha_p2;  // ... times *alpha_p2 (device, null = 1)
+    float hscale;  // shadow = cvt16(out * hscale * *hscale_p)
+    const float* hscale_p;
+    int bf16;     // 0 = fp16 operands/shadow, 1 = bf16
+    int* status;  // device word; bit 0 set when a shadow value overflowed the 16-bit range
+};
+
+// Build a 2-D TMA map (SWIZZLE_128B, 16-bit elements) over a column-major parent array with `rows` x `cols`
+// elements and leading dimension `ld`; a box is box_rows (contiguous) x box_cols.
+int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols);
+
+// Box shapes each variant expects for its A and B maps.
+void gemm_box_shapes(int variant, uint32_t* a_box_rows, uint32_t* a_box_cols, uint32_t* b_box_rows,
+                     uint32_t* b_box_cols);
+
+// Launch on `stream` using at most `max_sms` SMs (0 = all).  Returns cudaError_t as int.
+int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
+                   cudaStream_t stream);
+
+}  // namespace mplu

@@ -1,0 +1,40 @@
+// Internal launch interface shared by the CUDA translation units of libmplu (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mplu {
+
+// indices into the device-resident scale table (all powers of two; 1 for bf16)
+enum ScaleIdx : int {
+    SC_A = 0,           // scale of matrix-magnitude (A / U type) 16-bit shadows
+    SC_A_INV = 1,       // 1 / SC_A
+    SC_L = 2,           // scale of multiplier (L type) shadows
+    SC_L_INV = 3,       // 1 / SC_L
+    SC_NEG_LA_INV = 4,  // -1 / (SC_L * SC_A): alpha of the Schur update
+    SC_ONE = 5,
+    SC_COUNT = 8
+};
+
+constexpr int kDiagBlock = 128;  // diagonal block / base panel width
+
+// panel.cu
+int launch_first_touch(const double* A, long long lda, int n, float* W, long long ldw, int npad, float* amax,
+                       double* rowsum_part, int nchunk, double* anorm, cudaStream_t st);
+int launch_scales(const float* amax, float* scales, int target_exp_a, int exp_l, int bf16, cudaStream_t st);
+int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, int rows, int cols, const float* scale,
+                       int bf16, int* status, cudaStream_t st);
+// inv_scales[4*blk + {0,1,2,3}] = {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv}
+int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, float* Linv32, float* Uinv32,
+                   float* inv_scales, int blk, int bf16, int* status, cudaStream_t st);
+
+// ir.cu
+// r = b - A*x (fp64), ||r||_inf and ||x||_inf into norms[0], norms[1]
+int launch_residual(const double* A, long long lda, int n, const double* x, const double* b, double* r,
+                    double* partial, int nchunk, double* norms, cudaStream_t st);
+// solve L U d = r with the fp32 factors in W (unit-lower L, U), blocked by kDiagBlock with the fp32 inverses of the
+// diagonal blocks; y (fp32 work vector of length npad).  d_out (fp64) = solution; if x_accum != null, x_accum += d.
+int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
+                    const double* rhs, float* y, double* d_out, double* x_accum, cudaStream_t st);
+
+}  // namespace mplu
