@@ -108,6 +108,11 @@ int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *
 int mplu_residual(int n, const double *dA, long long lda, const double *dx, const double *db, double *dr,
                   double *dnorms, void *stream);
 
+/* Synthetic input in device memory: a(i,j) = (splitmix64(seed<<40 | i<<20 | j) % 100) / 10 -- the value set of the
+ * reference generator (matrix_generator.cpp:66) -- with, if `dominant`, the diagonal replaced by the column's
+ * off-diagonal sum + 1.  db (optional) receives b = A * ones. */
+int mplu_generate(int n, unsigned long long seed, int dominant, double *dA, long long lda, double *db, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

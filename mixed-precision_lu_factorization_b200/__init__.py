@@ -76,6 +76,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.mplu_gemm16.argtypes = [i, i, i, i, i, f, vp, ll, vp, ll, f, vp, ll, vp, ll, f, i, vp]
     lib.mplu_diag_lu128.argtypes = [vp, ll, vp, vp, vp]
     lib.mplu_residual.argtypes = [i, vp, ll, vp, vp, vp, vp, vp]
+    lib.mplu_generate.argtypes = [i, C.c_ulonglong, i, vp, ll, vp, vp]
+    lib.mplu_generate.restype = i
     for name in ("mplu_create", "mplu_factor_device", "mplu_solve_device", "mplu_gesv_device", "mplu_gesv_host",
                  "mplu_get_factors", "mplu_gemm16", "mplu_diag_lu128", "mplu_residual"):
         getattr(lib, name).restype = i
@@ -197,3 +199,15 @@ def gemm16(variant, A, B, C_io=None, alpha=1.0, beta=0.0, want_shadow=False, hsc
     _check(rc, "mplu_gemm16")
     torch.cuda.synchronize()
     return (C_io, H) if want_shadow else C_io
+
+
+def generate(n, seed=1, dominant=True, with_rhs=True):
+    """Device-resident synthetic system (column-major fp64 A, b = A*1) -- same formula as the oracle's counter_matrix."""
+    import torch
+    A = torch.empty(n, n, dtype=torch.float64, device="cuda").t()
+    b = torch.empty(n, dtype=torch.float64, device="cuda") if with_rhs else None
+    torch.cuda.synchronize()
+    _check(load_library().mplu_generate(n, seed, 1 if dominant else 0, A.data_ptr(), n,
+                                        b.data_ptr() if with_rhs else None, None), "mplu_generate")
+    torch.cuda.synchronize()
+    return A, b

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-I", str(ROOT / "include"),
 ]
 
-SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "mpf_compat.cu"]
+SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "generate.cu", "mpf_compat.cu"]
 
 
 def _nvcc() -> str:

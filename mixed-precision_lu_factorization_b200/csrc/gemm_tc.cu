@@ -6,8 +6,8 @@
 //
 // Replaces the rank-r cublasDgemm / cublasDtrsm pair of the reference (/root/reference/MPF.cu:215-239).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32*w..32*w+31), warp 4 TMA producer, warp 5 TMEM
-// allocator + MMA issuer.  Persistent: each CTA (or CTA pair, cta_group::2) walks tiles t, t+G, t+2G, ...
+// Warp roles (320 threads): warps 0-7 epilogue (TMEM lanes 32*(w%4).., column half w/4), warp 8 TMA producer,
+// warp 9 TMEM allocator + MMA issuer.  Persistent: each CTA (or CTA pair, cta_group::2) walks tiles t, t+G, t+2G, ...
 #include "gemm_tc.h"
 #include "ptx.cuh"
 
@@ -24,7 +24,8 @@ constexpr int BN = 256;  // UMMA N (accumulator columns per stage)
 constexpr int BK = 64;   // K elements per smem stage (= one 128-byte swizzle row)
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int GROUP_M = 8;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;   // 2 column halves x 4 TMEM lane quarters
+constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
 template <int kCG>
 struct Cfg {
@@ -44,6 +45,63 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mt
     const int r = t - g * group_size;
     mt = first_m + r % gm;
     nt = r / gm;
+}
+
+// ---- epilogue helpers: one 32-column chunk of one row per thread.  kFull = the whole 32x32 patch is in range, so
+// the hot path carries no per-element predicates or branches (the first version of this epilogue was 13.7k SASS
+// instructions and instruction-fetch bound: profiles/r01_gemm_epilogue_v1.txt).
+template <bool kFull>
+__device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, int row, int col0) {
+    if (p.Cin64) {
+        const double* src = p.Cin64 + row + (long long)col0 * p.ldc64;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            dst[j] = (kFull || (row < p.M && col0 + j < p.N)) ? static_cast<float>(__ldg(src + (long long)j * p.ldc64)) : 0.f;
+    } else {
+        const float* src = p.Cin + row + (long long)col0 * p.ldcin;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            dst[j] = (kFull || (row < p.M && col0 + j < p.N)) ? src[(long long)j * p.ldcin] : 0.f;
+    }
+}
+
+template <bool kFull>
+__device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (&cin)[32], const GemmParams& p,
+                                          float alpha, float hs, float hmax, int row, int wrow0, int col0, bool& ovf) {
+    float out[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = fmaf(alpha, __uint_as_float(v[j]), cin[j]);
+    if (p.C) {
+        float* dst = p.C + row + (long long)col0 * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (kFull || (row < p.M && col0 + j < p.N)) dst[(long long)j * p.ldc] = out[j];
+    }
+    if (p.H && (wrow0 < p.h_rows || col0 < p.h_cols)) {  // warp-uniform reject of chunks outside the shadow region
+        const bool row_in = row < p.h_rows;
+        if (p.bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.H) + row + (long long)col0 * p.ldh;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float hv = out[j] * hs;
+                if ((kFull || (row < p.M && col0 + j < p.N)) && (row_in || col0 + j < p.h_cols))
+                    dst[(long long)j * p.ldh] = __float2bfloat16_rn(hv);
+            }
+        } else {
+            __half* dst = reinterpret_cast<__half*>(p.H) + row + (long long)col0 * p.ldh;
+            float mx = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float hv = out[j] * hs;
+                if ((kFull || (row < p.M && col0 + j < p.N)) && (row_in || col0 + j < p.h_cols)) {
+                    dst[(long long)j * p.ldh] = __float2half_rn(hv);
+                    mx = fmaxf(mx, fabsf(hv));
+                    ovf |= (hv != hv);
+                }
+            }
+            ovf |= (mx > hmax);
+        }
+    }
 }
 
 template <int kCG, bool kAMN>
@@ -67,7 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t cta_rank = 0;
     if constexpr (kCG == 2) cta_rank = ptx::cluster_ctarank();
 
-    if (warp == 4 && lane == 0) {
+    if (warp == EPI_WARPS && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
         for (int i = 0; i < C::STAGES; ++i) {
@@ -76,12 +134,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], 1);         // one tcgen05.commit
-            ptx::mbar_init(&tempty[i], 4 * kCG);  // one arrival per epilogue warp per CTA (leader's barrier)
+            ptx::mbar_init(&tempty[i], EPI_WARPS * kCG);  // one arrival per epilogue warp per CTA (leader's barrier)
         }
         ptx::fence_mbar_init();
     }
     if constexpr (kCG == 2) ptx::cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
-    if (warp == 5) ptx::tmem_alloc<kCG>(tmem_slot, 512);
+    if (warp == EPI_WARPS + 1) ptx::tmem_alloc<kCG>(tmem_slot, 512);
     ptx::tc_fence_before();
     if constexpr (kCG == 2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
@@ -94,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int first_tile = blockIdx.x / kCG;
     const int tile_step = gridDim.x / kCG;
 
-    if (warp == 4) {
+    if (warp == EPI_WARPS) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -136,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
         if (cta_rank == 0) {
             const uint32_t idesc = make_idesc_f16(BM * kCG, BN, p.bf16 != 0, kAMN, false);
@@ -176,72 +234,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue warps 0..3
+        // ------------------------------------------------------------ epilogue warps 0..7
+        // warp w: TMEM lanes 32*(w%4).. (rows), columns [128*(w/4), +128) of the tile in 4 chunks of 32.
+        // The addend C is software-prefetched one chunk ahead (also across tiles, i.e. while the MMAs of this
+        // tile are still running) so that each warp keeps 2 x 32 x 128 B of loads in flight.
         float alpha = p.alpha;
         if (p.alpha_p1) alpha *= __ldg(p.alpha_p1);
         if (p.alpha_p2) alpha *= __ldg(p.alpha_p2);
         float hs = p.hscale;
         if (p.hscale_p) hs *= __ldg(p.hscale_p);
         const float hmax = p.bf16 ? 3.0e38f : 65504.f;
+        const uint32_t q = warp & 3, half = warp >> 2;
+        const bool has_cin = (p.Cin != nullptr) || (p.Cin64 != nullptr);
         bool ovf = false;
+
+        float cinA[32], cinB[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { cinA[j] = 0.f; cinB[j] = 0.f; }
         uint32_t iter = 0;
-        for (int t = first_tile; t < num_tiles; t += tile_step, ++iter) {
-            int mt, nt;
+        int t = first_tile;
+        int mt = 0, nt = 0;
+        if (t < num_tiles) {
             tile_coords(t, num_m, num_n, mt, nt);
+            if (has_cin) {
+                const int wrow0 = mt * BM * kCG + cta_rank * BM + q * 32, c0 = nt * BN + half * 128;
+                if (wrow0 + 32 <= p.M && c0 + 32 <= p.N) epi_load<true>(cinA, p, wrow0 + lane, c0);
+                else epi_load<false>(cinA, p, wrow0 + lane, c0);
+            }
+        }
+        for (; t < num_tiles; t += tile_step, ++iter) {
             const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+            const int wrow0 = mt * BM * kCG + cta_rank * BM + q * 32;
+            const int row = wrow0 + lane;
+            const int colbase = nt * BN + half * 128;
+            const bool full = (wrow0 + 32 <= p.M) && (colbase + 128 <= p.N);  // warp-uniform
+            // next tile (for the cross-tile prefetch)
+            const int tn = t + tile_step;
+            int mtn = 0, ntn = 0;
+            if (tn < num_tiles) tile_coords(tn, num_m, num_n, mtn, ntn);
+
             ptx::mbar_wait(&tfull[as], aphase);
             ptx::tc_fence_after();
-            const int row = mt * BM * kCG + cta_rank * BM + warp * 32 + lane;
-            const bool row_ok = row < p.M;
-            const bool warp_rows_ok = (mt * BM * kCG + (int)cta_rank * BM + (int)warp * 32) < p.M;
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BN + half * 128;
+            uint32_t v[32];
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = nt * BN + c * 32;
-                if (col0 >= p.N || !warp_rows_ok) break;  // warp-uniform
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem_base + ((warp * 32u) << 16) + as * BN + c * 32, v);
-                float cin[32];
-                if (p.Cin64) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        cin[j] = (row_ok && col < p.N) ? static_cast<float>(__ldg(p.Cin64 + row + (long long)col * p.ldc64))
-                                                        : 0.f;
-                    }
-                } else if (p.Cin) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        cin[j] = (row_ok && col < p.N) ? p.Cin[row + (long long)col * p.ldcin] : 0.f;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) cin[j] = 0.f;
+            for (int c = 0; c < 128; c += 64) {
+                // chunk c (addend in cinA); prefetch chunk c+32 into cinB
+                ptx::tmem_ld_32x32(taddr + c, v);
+                if (has_cin) {
+                    if (full) epi_load<true>(cinB, p, row, colbase + c + 32);
+                    else epi_load<false>(cinB, p, row, colbase + c + 32);
                 }
                 ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = col0 + j;
-                    if (row_ok && col < p.N) {
-                        const float out = fmaf(alpha, __uint_as_float(v[j]), cin[j]);
-                        if (p.C) p.C[row + (long long)col * p.ldc] = out;
-                        if (p.H && (row < p.h_rows || col < p.h_cols)) {
-                            const float hv = out * hs;
-                            ovf |= !(fabsf(hv) <= hmax);
-                            if (p.bf16)
-                                reinterpret_cast<__nv_bfloat16*>(p.H)[row + (long long)col * p.ldh] = __float2bfloat16_rn(hv);
-                            else
-                                reinterpret_cast<__half*>(p.H)[row + (long long)col * p.ldh] = __float2half_rn(hv);
-                        }
+                if (full) epi_store<true>(v, cinA, p, alpha, hs, hmax, row, wrow0, colbase + c, ovf);
+                else epi_store<false>(v, cinA, p, alpha, hs, hmax, row, wrow0, colbase + c, ovf);
+                // chunk c+32 (cinB); prefetch chunk c+64 -- or the next tile's first chunk -- into cinA
+                ptx::tmem_ld_32x32(taddr + c + 32, v);
+                if (has_cin) {
+                    if (c == 0) {
+                        if (full) epi_load<true>(cinA, p, row, colbase + 64);
+                        else epi_load<false>(cinA, p, row, colbase + 64);
+                    } else if (tn < num_tiles) {
+                        const int wrow0n = mtn * BM * kCG + cta_rank * BM + q * 32, c0n = ntn * BN + half * 128;
+                        if (wrow0n + 32 <= p.M && c0n + 32 <= p.N) epi_load<true>(cinA, p, wrow0n + lane, c0n);
+                        else epi_load<false>(cinA, p, wrow0n + lane, c0n);
                     }
                 }
+                ptx::tmem_ld_wait();
+                if (c == 64) {
+                    // accumulator fully read: hand the TMEM stage back before the last stores
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (kCG == 1) ptx::mbar_arrive(&tempty[as]);
+                        else ptx::mbar_arrive_cluster(&tempty[as], 0);
+                    }
+                }
+                if (full) epi_store<true>(v, cinB, p, alpha, hs, hmax, row, wrow0, colbase + c + 32, ovf);
+                else epi_store<false>(v, cinB, p, alpha, hs, hmax, row, wrow0, colbase + c + 32, ovf);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (kCG == 1) ptx::mbar_arrive(&tempty[as]);
-                else ptx::mbar_arrive_cluster(&tempty[as], 0);
-            }
+            mt = mtn; nt = ntn;
         }
         if (p.status && __any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.status, 1);
     }
@@ -249,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------------------------- teardown
     ptx::tc_fence_before();
     if constexpr (kCG == 2) ptx::cluster_sync_all(); else __syncthreads();
-    if (warp == 5) ptx::tmem_dealloc<kCG>(tmem_base, 512);
+    if (warp == EPI_WARPS + 1) ptx::tmem_dealloc<kCG>(tmem_base, 512);
 }
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -109,6 +109,22 @@ def gesv(ns=(256, 1024, 4096), nb=1024, variant=-1, prec=0):
         del A, Acm
 
 
+def gesv_dev(ns=(8192,), nb=1024, variant=-1, prec=0, reps=2):
+    s = m.Solver(0)
+    for n in ns:
+        A, b = m.generate(n, seed=1)
+        opts = m.default_options(nb=nb, gemm_variant=variant, precision=prec)
+        for rep in range(reps):
+            try:
+                x, st = s.gesv(A, b, opts, allow_noconv=True)
+                d = st.as_dict()
+                print(f"gesv n={n} nb={nb} var={variant} prec={prec} rep={rep}: iters {d['iters']} conv {d['converged']} be {d['backward_error']:.2e} first {d['first_backward_error']:.2e} "
+                      f"status {d['status_bits']} factor {d['factor_ms']:.2f} ms solve {d['solve_ms']:.2f} ms  TF {2/3*n**3/d['total_ms']/1e9:.2f} (factor only {2/3*n**3/d['factor_ms']/1e9:.2f}) launches {d['kernel_launches']} gemms {d['gemm_launches']} fwd err {(x-1).abs().max().item():.2e}", flush=True)
+            except Exception as e:
+                print(f"gesv n={n}: EXC {e}", flush=True)
+        del A, b
+
+
 def ref(ns=(256, 1024, 4096)):
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libmpf_ref.so"))
     f = getattr(lib, "_Z3MPFPdiiPi")
