@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- LU+IR TFLOP/s (2/3 n^3) of the mixed-precision solver on synthetic diagonally dominant systems.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 32768] [--impl reference]
+
+A "step" is one full solve of one n x n system: no-pivot LU in fp16 (fp32 accumulate) on the tcgen05 tensor cores +
+fp64 iterative refinement to the dsgesv tolerance, inputs (fp64 A, b) already resident in HBM (`value`).  `e2e` is the
+same solve through the C-ABI host entry point mplu_gesv_host(): pinned host A and b copied to the device and x copied
+back inside the timed region.  One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG_NAME = "mixed-precision_lu_factorization_b200"
+METRIC = "LU+IR TFLOP/s (2/3*n^3)"
+
+
+def flops(n):
+    return 2.0 / 3.0 * float(n) ** 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        # "under load": upper half of the samples
+        load = sm[len(sm) // 2:] if sm else []
+        return dict(sm_mhz=(load[len(load) // 2] if load else None), sm_max_mhz=(max(mx) if mx else None), reasons=reasons,
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_lapack_baseline(n_sample):
+    """Host LAPACK dgetrf + dgetrs on all host cores (the reference's CPU arm: LAPACKE_dgetrf at benchmark.cpp:240,
+    plus the solve the metric adds), on a bounded sample size; TFLOP/s by the same 2/3 n^3 count."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import mplu_oracle as orc
+    from scipy.linalg import lu_factor, lu_solve
+    A = orc.counter_matrix(n_sample, seed=1)
+    b = A.sum(axis=1)
+    lu_factor(A[:512, :512].copy())  # thread-pool warm-up
+    t = time.perf_counter()
+    lu, piv = lu_factor(A, check_finite=False)
+    x = lu_solve((lu, piv), b, check_finite=False)
+    dt = time.perf_counter() - t
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info
+        th = [i["num_threads"] for i in threadpool_info() if i.get("internal_api") == "openblas"]
+        cores = max(th) if th else cores
+    except Exception:
+        pass
+    err = float(np.abs(x - 1).max())
+    return dict(value=flops(n_sample) / dt / 1e12, unit="TFLOP/s", cores=cores, kind="reference",
+                sample=f"scipy/OpenBLAS dgetrf+dgetrs, n={n_sample}, {dt:.2f} s, max|x-1|={err:.1e}")
+
+
+def run_reference(args):
+    """--impl reference: the UNMODIFIED reference MPF() (oracle/_ref/libmpf_ref.so, built from /root/reference by
+    oracle/Makefile; CUDA path, r = 32 as benchmark.cpp:220) timed as benchmark.cpp:219-222 times it (whole call,
+    host buffers), next to host LAPACK on the box's cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ctypes
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mplu_oracle as orc
+    n = args.n
+    n_cpu = min(n, 8192)
+    cpu = cpu_lapack_baseline(n_cpu)
+    line = dict(impl="reference", metric=METRIC, unit="TFLOP/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=f"n={n} column-diagonally-dominant, reference MPF(A,n,32,ipiv) LU only (it has no solve)"))
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libmpf_ref.so")
+    have_gpu = False
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    if os.path.exists(lib_path) and have_gpu:
+        lib = ctypes.CDLL(lib_path)
+        f = getattr(lib, "_Z3MPFPdiiPi")
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        f.restype = None
+        n_ref = min(n, args.ref_n)
+        A0 = np.asfortranarray(orc.counter_matrix(n_ref, seed=1))
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        times = []
+        for it in range(args.warmup + args.steps):
+            A = A0.copy(order="F")
+            ipiv = np.arange(1, n_ref + 1, dtype=np.int32)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(devnull, 1)  # MPF prints a line per panel
+            t = time.perf_counter()
+            f(A.ctypes.data, n_ref, 32, ipiv.ctypes.data)
+            dt = time.perf_counter() - t
+            os.dup2(saved, 1)
+            os.close(saved)
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        val = flops(n_ref) / (ms * 1e-3) / 1e12
+        line.update(value=val, ms_per_step=ms,
+                    cpu_baseline=dict(value=val, unit="TFLOP/s", cores=1, kind="reference",
+                                      sample=f"unmodified reference MPF() via oracle/_ref/libmpf_ref.so, n={n_ref}, r=32, one host "
+                                             f"thread driving the GPU, whole call incl. cudaMalloc/H2D/D2H as benchmark.cpp:219-222"),
+                    host_lapack=cpu,
+                    e2e=dict(value=val, unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    reference_arm=dict(kind="reference CUDA path (unmodified MPF.cu, -O3 sm_100a)", n=n_ref,
+                                       non_identity_pivots=int((ipiv != np.arange(1, n_ref + 1)).sum())))
+        line["config"]["workload"] = f"n={n_ref} column-diagonally-dominant, reference MPF(A,n,32,ipiv) (LU only; it has no solve)"
+    else:
+        line.update(value=cpu["value"], ms_per_step=None, cpu_baseline=cpu,
+                    e2e=dict(value=cpu["value"], unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        line["config"]["workload"] = cpu["sample"]
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default for this n)")
+    ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
+    ap.add_argument("--impl", choices=["mplu", "reference"], default="mplu")
+    ap.add_argument("--ref-n", type=int, default=16384, help="size the reference arm runs (bounded: it needs seconds per call)")
+    ap.add_argument("--cpu-n", type=int, default=8192, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "mplu" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    m = importlib.import_module(PKG_NAME)
+    pk = peaks()
+    n = args.n
+    opts = m.default_options(precision=1 if args.precision == "bf16" else 0)
+    if args.nb:
+        opts.nb = args.nb
+    elif n >= 16384:
+        opts.nb = 2048
+
+    # N > 1: the ranks solve independent systems (replicas, weak scaling) -- the 2D block-cyclic single-system path
+    # is described in DESIGN.md section 7 and not yet wired into bench.py.
+    solver = m.Solver(local)
+    A, b = m.generate(n, seed=1 + rank)
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+
+    def step():
+        return solver.gesv_ptr(n, A.data_ptr(), n, b.data_ptr(), x.data_ptr(), opts)
+
+    for _ in range(args.warmup):
+        st = step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(solver.stream)
+    tr_ms = tr_fl = tr_by = 0.0
+    tr_n = launches = iters = 0
+    worst_be = 0.0
+    with torch.cuda.stream(stream):
+        e0.record()
+        for _ in range(args.steps):
+            st = step()
+            tr_ms += st.trailing_ms; tr_fl += st.trailing_flops; tr_by += st.trailing_bytes; tr_n += st.trailing_launches
+            launches += st.kernel_launches
+            iters = max(iters, st.iters)
+            worst_be = max(worst_be, st.backward_error)
+        e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    fwd_err = float((x - 1).abs().max().item())
+
+    # ---- e2e: host buffers through mplu_gesv_host (pinned memory), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hA = torch.empty(n, n, dtype=torch.float64, pin_memory=True)
+        hA.copy_(A.t())  # A is column-major n x n: its transpose view is the contiguous storage
+        hb = b.cpu().pin_memory()
+        hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        solver.gesv_host_ptr(n, hA.data_ptr(), n, hb.data_ptr(), hx.data_ptr(), opts)  # warm-up (staging alloc)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        k_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            st_h = solver.gesv_host_ptr(n, hA.data_ptr(), n, hb.data_ptr(), hx.data_ptr(), opts)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / k_e2e
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = dict(value=world * flops(n) / float(t.item()) / 1e12, unit="TFLOP/s", h2d_bytes_per_step=8 * n * n + 8 * n,
+                   d2h_bytes_per_step=8 * n, ms_per_step=1e3 * float(t.item()), h2d_ms=st_h.h2d_ms,
+                   max_abs_err=float((hx - 1).abs().max().item()))
+        del hA
+
+    if rank == 0:
+        value = world * flops(n) / (ms_max * 1e-3) / 1e12
+        ach = (tr_fl / (tr_ms * 1e-3) / 1e12) if tr_ms > 0 else None
+        line = dict(metric=METRIC, value=value, unit="TFLOP/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_max, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=args.precision + " operands, f32 accumulate, f64 refinement", data="synthetic",
+                    config=dict(workload=f"n={n} mixed-precision LU+IR on 1 B200 per rank (BASELINE.json configs[2])" if n == 32768
+                                else f"n={n} mixed-precision LU+IR", n=n, nb=int(opts.nb), rhs=1,
+                                matrix="column-diagonally-dominant, values k/10 (reference generator distribution), seed=1+rank",
+                                l2_policy="inputs larger than L2 (A is %.1f GiB)" % (8.0 * n * n / 2 ** 30),
+                                parallelism=("replicas x%d" % world) if world > 1 else "single GPU"),
+                    ir_iters=iters, backward_error=worst_be, max_abs_err=fwd_err,
+                    factor_ms=st.factor_ms, solve_ms=st.solve_ms,
+                    gpu_launches=launches, clocks=clocks, e2e=e2e,
+                    roofline=dict(bound="tensor", kernel="gemm_tc_kernel (rank-nb trailing update)", achieved=ach,
+                                  peak=pk["tc_sustained"], unit="TFLOP/s", frac=(ach / pk["tc_sustained"]) if ach else None,
+                                  peak_kind=f"bf16_tflops_sustained ({pk['src']}); burst {pk['tc_burst']}",
+                                  launches=tr_n, avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
+                                  share_of_step=(tr_ms / args.steps / ms) if ms > 0 else None,
+                                  algorithmic_c_bytes_per_s=(tr_by / (tr_ms * 1e-3) / 1e9) if tr_ms > 0 else None,
+                                  traffic=None),
+                    headline_frac_of_peak=value / world / pk["tc_sustained"])
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = dict(cpu_lapack_baseline(min(n, args.cpu_n)), kind="port")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

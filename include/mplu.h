@@ -61,6 +61,10 @@ typedef struct mplu_stats {
     float h2d_ms, d2h_ms;   /* host variant only */
     int gemm_launches;      /* tcgen05 GEMM launches in the factorization */
     int kernel_launches;    /* all kernel launches (factor + solve) */
+    int trailing_launches;  /* rank-nb trailing updates among them (the dominant kernel) */
+    float trailing_ms;      /* summed device time of those launches (CUDA events on the launching stream) */
+    double trailing_flops;  /* their algorithmic flops, 2*M*N*K each */
+    double trailing_bytes;  /* their algorithmic C traffic, 8*M*N bytes each (fp32 read + write) */
 } mplu_stats;
 
 void mplu_default_options(mplu_options *opts);
@@ -107,6 +111,11 @@ int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *
 /* r = b - A x in fp64; norms[0] = ||r||_inf, norms[1] = ||x||_inf (device array of 2 doubles). */
 int mplu_residual(int n, const double *dA, long long lda, const double *dx, const double *db, double *dr,
                   double *dnorms, void *stream);
+
+/* Cooperative launches of the drop-in kernels HGETF2_kernel / dgetf2_native_npv (include/hgetf2_kernel.h,
+ * include/dgetf2_native_npv.h) with the reference caller's geometry, on device-resident column-major panels. */
+int mplu_hgetf2(void *d_panel_fp16, int ld, int rows, int cols, int *d_ipiv_panel, void *stream);
+int mplu_dgetf2_npv(int m, int n, double *d_panel, int ld, void *stream);
 
 /* Synthetic input in device memory: a(i,j) = (splitmix64(seed<<40 | i<<20 | j) % 100) / 10 -- the value set of the
  * reference generator (matrix_generator.cpp:66) -- with, if `dominant`, the diagonal replaced by the column's

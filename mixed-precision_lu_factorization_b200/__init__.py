@@ -35,7 +35,8 @@ class Stats(C.Structure):
                 ("rnorm_inf", C.c_double), ("backward_error", C.c_double), ("first_backward_error", C.c_double),
                 ("factor_ms", C.c_float), ("solve_ms", C.c_float), ("total_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("gemm_launches", C.c_int),
-                ("kernel_launches", C.c_int)]
+                ("kernel_launches", C.c_int), ("trailing_launches", C.c_int), ("trailing_ms", C.c_float),
+                ("trailing_flops", C.c_double), ("trailing_bytes", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -81,9 +82,12 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     for name in ("mplu_create", "mplu_factor_device", "mplu_solve_device", "mplu_gesv_device", "mplu_gesv_host",
                  "mplu_get_factors", "mplu_gemm16", "mplu_diag_lu128", "mplu_residual"):
         getattr(lib, name).restype = i
-    if hasattr(lib, "mplu_MPF"):
-        lib.mplu_MPF.argtypes = [vp, i, i, vp]
-        lib.mplu_MPF.restype = i
+    lib.mplu_MPF.argtypes = [vp, i, i, vp]
+    lib.mplu_MPF.restype = i
+    lib.mplu_hgetf2.argtypes = [vp, i, i, i, vp, vp]
+    lib.mplu_hgetf2.restype = i
+    lib.mplu_dgetf2_npv.argtypes = [i, i, vp, i, vp]
+    lib.mplu_dgetf2_npv.restype = i
     if path is None:
         _lib = lib
     return lib
@@ -211,3 +215,15 @@ def generate(n, seed=1, dominant=True, with_rhs=True):
                                         b.data_ptr() if with_rhs else None, None), "mplu_generate")
     torch.cuda.synchronize()
     return A, b
+
+
+def MPF(A, r=32, ipiv=None):
+    """Reference-compatible entry point (/root/reference/MPF.h:3): factor the column-major fp64 HOST matrix `A`
+    (numpy, Fortran order, modified in place) with panel width r; returns the 1-based pivot vector."""
+    import numpy as np
+    assert A.dtype == np.float64 and A.flags.f_contiguous and A.shape[0] == A.shape[1]
+    n = A.shape[0]
+    if ipiv is None:
+        ipiv = np.arange(1, n + 1, dtype=np.int32)  # benchmark.cpp:215-217
+    _check(load_library().mplu_MPF(A.ctypes.data, n, r, ipiv.ctypes.data), "MPF")
+    return ipiv

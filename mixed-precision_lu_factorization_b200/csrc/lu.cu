@@ -48,6 +48,11 @@ struct mplu_context {
     // tensor maps
     CUtensorMap tmWh_A, tmWh_B1, tmWh_B2, tmLinv_A, tmUinv_B1, tmUinv_B2;
     int gemm_launches = 0, kernel_launches = 0;
+    // per-launch timing of the trailing updates (events are cheap: <= npad/nb pairs per factorization)
+    static constexpr int kMaxTrail = 1024;
+    cudaEvent_t trail_ev[2 * kMaxTrail] = {};
+    int trail_count = 0;
+    double trail_flops = 0, trail_bytes = 0;
 };
 
 namespace {
@@ -156,6 +161,8 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     cudaStream_t st = c->stream;
     c->gemm_launches = 0;
     c->kernel_launches = 0;
+    c->trail_count = 0;
+    c->trail_flops = c->trail_bytes = 0;
     CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
 
     CKI(launch_first_touch(dA, lda, n, c->W, ld, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
@@ -217,7 +224,19 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
         const int Mt = npad - kend;
         if (Mt > 0) {
             GemmCall s{0, kend, k, 0, k, kend, Mt, Mt, nbk, kend, kend, true, sNeg, nullptr, sA, NB, NB};
+            const bool timed = c->trail_count < mplu_context::kMaxTrail;
+            if (timed) {
+                cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
+                if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
+                CK(cudaEventRecord(e0, st));
+            }
             CKI(run_gemm(c, s));
+            if (timed) {
+                CK(cudaEventRecord(c->trail_ev[2 * c->trail_count + 1], st));
+                c->trail_count++;
+                c->trail_flops += 2.0 * Mt * (double)Mt * nbk;
+                c->trail_bytes += 8.0 * Mt * (double)Mt;
+            }
         }
     }
     c->factored = true;
@@ -291,6 +310,15 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
         stats->first_backward_error = first_be;
         stats->gemm_launches = c->gemm_launches;
         stats->kernel_launches = c->kernel_launches;
+        stats->trailing_launches = c->trail_count;
+        stats->trailing_flops = c->trail_flops;
+        stats->trailing_bytes = c->trail_bytes;
+        float tms = 0.f;
+        for (int i = 0; i < c->trail_count; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->trail_ev[2 * i], c->trail_ev[2 * i + 1]) == cudaSuccess) tms += ms;
+        }
+        stats->trailing_ms = tms;
     }
     if (converged) return 0;
     if (h_status & 1) return MPLU_E_OVERFLOW;
@@ -343,6 +371,7 @@ void mplu_destroy(mplu_context* c) {
     cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

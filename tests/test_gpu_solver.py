@@ -1,0 +1,145 @@
+"""GPU parity tests of the hot path through the C ABI: no-pivot mixed-precision LU + fp64 iterative refinement vs
+the oracle, host LAPACK and the golden outputs of the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps / 2  # unit roundoff
+
+
+def cm(t):
+    return t.t().contiguous().t()
+
+
+def run(mplu, solver, A, b, **kw):
+    import torch
+    dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
+    db = torch.tensor(b, dtype=torch.float64, device="cuda")
+    x, st = solver.gesv(dA, db, mplu.default_options(**kw))
+    return x.cpu().numpy(), st.as_dict()
+
+
+@pytest.mark.parametrize("n", [1024])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_config1_n1024_vs_lapack_and_oracle(mplu, oracle, solver, n, precision):
+    """BASELINE.json configs[0]: n=1024 diagonally dominant, no-pivot LU + IR single RHS vs host dgetrf/dgetrs."""
+    A = oracle.counter_matrix(n, seed=1)
+    b = A.sum(axis=1)
+    x, st = run(mplu, solver, A, b, precision=precision)
+    x_ref, lu_ref, piv = oracle.lapack_gesv(A, b)
+    assert np.array_equal(piv, np.arange(n))
+    emu = oracle.refine(A, b, oracle.lu_mixed_emulated(A, 128, bf16=bool(precision)))
+    assert st["converged"] == 1 and st["status_bits"] == 0
+    assert st["iters"] <= emu["iters"]  # same or fewer refinement iterations than the emulated algorithm
+    assert st["backward_error"] <= 2 * n * EPS  # north_star: about 1e-15 * n
+    assert st["backward_error"] <= 4 * max(emu["backward_error"], EPS)
+    np.testing.assert_allclose(x, x_ref, rtol=0, atol=1e-12)
+    # LU factors vs the fp64 no-pivot LU (= what the reference returns on this input), stated fp16/bf16 tolerance:
+    # relative to max|U| a few unit roundoffs of the 16-bit type per 128-wide block step
+    LU = solver.factors(n).cpu().numpy()
+    u16 = 2.0 ** -11 if precision == 0 else 2.0 ** -8
+    assert np.abs(np.triu(LU) - np.triu(lu_ref)).max() <= 0.02 * u16 * np.abs(lu_ref).max()
+    assert np.abs(np.tril(LU, -1) - np.tril(lu_ref, -1)).max() <= 2 * u16 * np.abs(np.tril(lu_ref, -1)).max()
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_factors_vs_golden_reference_output(mplu, oracle, solver, n):
+    """Same generated input as the golden run of the unmodified reference MPF(): identity pivots there, so its output
+    is the fp64 no-pivot LU our low-precision factors approximate."""
+    g = np.load(os.path.join(GOLDEN, f"ref_mpf_dd_n{n}.npz"))
+    assert np.array_equal(g["ipiv"], np.arange(1, n + 1))
+    A = oracle.counter_matrix(n, seed=int(g["seed"]))
+    x, st = run(mplu, solver, A, A.sum(axis=1))
+    LU = solver.factors(n).cpu().numpy()
+    ref = g["LU"]
+    assert np.abs(np.triu(LU - ref)).max() <= 0.02 * 2.0 ** -11 * np.abs(ref).max()
+    assert np.abs(np.tril(LU - ref, -1)).max() <= 2 * 2.0 ** -11 * np.abs(np.tril(ref, -1)).max()
+    assert st["converged"] == 1 and np.abs(x - 1).max() < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 1000, 1537])
+def test_ragged_sizes(mplu, oracle, solver, n):
+    A = oracle.counter_matrix(n, seed=2)
+    b = A @ np.linspace(-1, 1, n)
+    x, st = run(mplu, solver, A, b, nb=512)
+    assert st["converged"] == 1
+    np.testing.assert_allclose(x, np.linspace(-1, 1, n), rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("nb", [128, 256, 1024, 2048])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_block_sizes_and_gemm_variants_agree(mplu, oracle, solver, nb, variant):
+    n = 2304
+    A = oracle.counter_matrix(n, seed=4)
+    b = A.sum(axis=1)
+    x, st = run(mplu, solver, A, b, nb=nb, gemm_variant=variant)
+    assert st["converged"] == 1 and st["iters"] <= 3
+    assert st["backward_error"] <= 2 * n * EPS
+    assert np.abs(x - 1).max() < 1e-11
+
+
+def test_solve_reuses_factors_for_new_rhs(mplu, oracle, solver):
+    import torch
+    n = 1024
+    A = oracle.counter_matrix(n, seed=9)
+    dA = cm(torch.tensor(A, device="cuda"))
+    torch.cuda.synchronize()
+    solver.factor_ptr(n, dA.data_ptr(), dA.stride(1), mplu.default_options())
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        xt = rng.standard_normal(n)
+        db = torch.tensor(A @ xt, device="cuda")
+        dx = torch.empty(n, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        st = solver.solve_ptr(dA.data_ptr(), dA.stride(1), db.data_ptr(), dx.data_ptr())
+        assert st.converged == 1
+        np.testing.assert_allclose(dx.cpu().numpy(), xt, rtol=0, atol=1e-11)
+
+
+def test_host_buffer_entry_point(mplu, oracle, solver):
+    n = 640
+    A = np.asfortranarray(oracle.counter_matrix(n, seed=11))
+    b = A.sum(axis=1)
+    x = np.empty(n)
+    st = solver.gesv_host_ptr(n, A.ctypes.data, n, b.ctypes.data, x.ctypes.data, mplu.default_options())
+    assert st.converged == 1 and st.h2d_ms > 0
+    np.testing.assert_allclose(x, 1.0, rtol=0, atol=1e-12)
+
+
+def test_spd_kappa_small(mplu, oracle, solver):
+    """config 5 at test size: SPD, kappa = 1e2, classic IR converges (oracle emulation: <= 4 iterations)."""
+    n = 1024
+    A = oracle.spd_kappa_matrix(n, 1e2, seed=3)
+    xt = np.ones(n)
+    b = A @ xt
+    emu = oracle.refine(A, b, oracle.lu_mixed_emulated(A, 128))
+    x, st = run(mplu, solver, A, b)
+    assert st["converged"] == 1 and st["iters"] <= emu["iters"] + 1
+    assert st["backward_error"] <= 2 * n * EPS
+
+
+def test_zero_pivot_and_nonconvergence_are_reported(mplu, solver):
+    n = 256
+    A = np.eye(n)
+    A[0, 0] = 0.0
+    A[0, 1] = A[1, 0] = 1.0  # needs pivoting: no-pivot LU hits an exact zero pivot
+    with pytest.raises(mplu.MpluError) as e:
+        run(mplu, solver, A, np.ones(n))
+    assert e.value.code in (-6, -7, -5)
+
+
+def test_full_size_properties_n32768(mplu, solver):
+    """BASELINE.json configs[2] through size-independent properties: refined solution reproduces x_true = 1,
+    fp64 normwise backward error about 1e-15*n or better, in at most 3 refinement iterations."""
+    n = 32768
+    A, b = mplu.generate(n, seed=1)
+    x, st = solver.gesv(A, b, mplu.default_options())
+    d = st.as_dict()
+    assert d["converged"] == 1 and d["status_bits"] == 0 and d["iters"] <= 3
+    assert d["backward_error"] <= 1e-15 * n
+    assert (x - 1).abs().max().item() <= 1e-11

@@ -1,0 +1,109 @@
+"""CPU tests: pin the oracle (generator vs libc rand(); factorization vs host LAPACK; restatement of the reference's
+MPF vs outputs of the unmodified reference captured on a B200 in tests/golden/)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+def test_glibc_rand_matches_libc(oracle):
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    ref = [libc.rand() for _ in range(5000)]
+    g = oracle.GlibcRand()
+    assert [g.rand() for _ in range(5000)] == ref
+
+
+def test_matrix_generator_first_matrix(oracle):
+    # SURVEY.md section 8b [probe]: first 2x2 emitted by the reference generator is 8.3 8.6 / 7.7 1.5
+    n, M = next(oracle.matrix_generator_stream(2))
+    assert n == 2
+    np.testing.assert_array_equal(M, np.array([[8.3, 8.6], [7.7, 1.5]]))
+    assert oracle.matrix_generator_sizes(1024, 2, "exp") == [2 ** k for k in range(1, 11)]
+    assert oracle.matrix_generator_sizes(10, 3, "lin") == [2, 5, 8]
+
+
+def test_double_to_fp16_contract(oracle):
+    x = np.array([1e6, -1e6, 65504.0, 6.0e-5, -6.0e-5, 6.2e-5, 0.1, 1.0 + 2 ** -11])
+    h = oracle.double_to_fp16(x).astype(np.float64)
+    assert h[0] == 65504.0 and h[1] == -65504.0 and h[2] == 65504.0  # saturates (fp16_utils.h:19-20)
+    assert h[3] == 0.0 and h[4] == 0.0 and h[5] != 0.0  # flush below 6.10352e-5 (fp16_utils.h:21)
+    assert h[6] == np.float64(np.float16(0.1)) and h[7] == 1.0  # RN, ties to even
+
+
+@pytest.mark.parametrize("n", [33, 64, 256])
+def test_mpf_reference_on_dominant_is_nopivot_lu(oracle, n):
+    from scipy.linalg import lu_factor
+    A = oracle.counter_matrix(n, seed=7)
+    LU, ipiv = oracle.mpf_reference(A, 32)
+    assert np.array_equal(ipiv, np.arange(1, n + 1))  # diagonal dominance => identity pivots
+    lu, piv = lu_factor(A)
+    assert np.array_equal(piv, np.arange(n))
+    np.testing.assert_allclose(LU, lu, rtol=0, atol=1e-12 * np.abs(lu).max())
+    assert oracle.check_correctitude(A, LU, ipiv)
+    np.testing.assert_allclose(oracle.lu_nopivot_fp64(A, 32), LU, rtol=0, atol=1e-12 * np.abs(lu).max())
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 65])
+def test_mpf_reference_random_passes_reference_check(oracle, n):
+    # edge sizes around the panel width r = 32, incl. N % r == 1 where MPF leaves IPIV[N-1] untouched (MPF.cu:104)
+    rng = np.random.default_rng(n)
+    A = (rng.integers(0, 100, size=(n, n)) / 10.0) + 0.0
+    LU, ipiv = oracle.mpf_reference(A, 32)
+    assert oracle.check_correctitude(A, LU, ipiv, tol=1e-9)
+    assert ipiv[n - 1] == n
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_golden_dominant_vs_oracle(oracle, n):
+    g = np.load(os.path.join(GOLDEN, f"ref_mpf_dd_n{n}.npz"))
+    A = oracle.counter_matrix(n, seed=int(g["seed"]))
+    LU, ipiv = oracle.mpf_reference(A, int(g["r"]))
+    assert np.array_equal(g["ipiv"], ipiv) and np.array_equal(ipiv, np.arange(1, n + 1))
+    np.testing.assert_allclose(g["LU"], LU, rtol=0, atol=1e-13 * np.abs(LU).max())
+    assert oracle.check_correctitude(A, g["LU"], g["ipiv"])
+
+
+def _stream_matrix(oracle, n):
+    for m_, M in oracle.matrix_generator_stream(n):
+        if m_ == n:
+            return oracle.as_benchmark_reads(M)
+    raise AssertionError
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_golden_random_pivoting_vs_oracle(oracle, n):
+    # fp16 pivot discovery on the reference generator's own stream: the restated HGETF2 reproduces the reference's
+    # pivot sequence exactly at these sizes (fused multiply-subtract, the -O3 code path)
+    g = np.load(os.path.join(GOLDEN, f"ref_mpf_rand_n{n}.npz"))
+    A = _stream_matrix(oracle, n)
+    LU, ipiv = oracle.mpf_reference(A, 32, fused=True)
+    assert np.array_equal(g["ipiv"], ipiv)
+    np.testing.assert_allclose(g["LU"], LU, rtol=0, atol=1e-11 * np.abs(LU).max())
+    assert oracle.check_correctitude(A, g["LU"], g["ipiv"])
+
+
+def test_golden_random_256_is_valid_factorization(oracle):
+    # at n=256 fp16 near-ties make the pivot sequence depend on the fp16 division's last bit; both the
+    # reference's and the oracle's factorizations must still satisfy the reference's own check
+    g = np.load(os.path.join(GOLDEN, "ref_mpf_rand_n256.npz"))
+    A = _stream_matrix(oracle, 256)
+    assert oracle.check_correctitude(A, g["LU"], g["ipiv"])
+    LU, ipiv = oracle.mpf_reference(A, 32)
+    assert oracle.check_correctitude(A, LU, ipiv)
+
+
+def test_emulated_mixed_lu_refines_to_fp64(oracle):
+    n = 512
+    A = oracle.counter_matrix(n, seed=1)
+    b = A.sum(axis=1)
+    for bf16 in (False, True):
+        W = oracle.lu_mixed_emulated(A, 128, bf16=bf16)
+        res = oracle.refine(A, b, W)
+        assert res["converged"] and res["iters"] <= 3
+        assert res["backward_error"] < 4 * n * 1.1e-16
+        x_ref, _, _ = oracle.lapack_gesv(A, b)
+        np.testing.assert_allclose(res["x"], x_ref, rtol=1e-12)
