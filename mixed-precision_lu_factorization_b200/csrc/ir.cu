@@ -81,62 +81,127 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
     }
 }
 
-__global__ void to_float_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, int npad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < npad) dst[i] = (i < n) ? static_cast<float>(src[i]) : 0.f;
-}
-
-__global__ void finish_solve_kernel(const float* __restrict__ sol, int n, double* __restrict__ d_out,
-                                    double* __restrict__ x_accum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const double d = static_cast<double>(sol[i]);
-        if (d_out) d_out[i] = d;
-        if (x_accum) x_accum[i] += d;
-    }
-}
-
-// One block-column step of a blocked triangular solve (column sweep).
-//   lower:  s = inv(L_jj) * y[j-block];  sol[j-block] = s;  y[r] -= L(r, j-block) * s   for rows r below the block
-//   upper:  s = inv(U_jj) * y[j-block];  sol[j-block] = s;  y[r] -= U(r, j-block) * s   for rows r above the block
-// Every CTA recomputes s (64 KiB of the fp32 inverse, L2 resident) so one launch does the whole step.
-constexpr int TS_THREADS = 256;
+// ---------------------------------------------------------------------------------------------------------------
+// lu_solve_kernel: both triangular solves of L U d = rhs in ONE cooperative launch (the previous version launched one
+// kernel per 128-column block: 2*n/128 dependent launches per solve, 15 ms of the n = 16384 step).
+//
+// Work unit ("step") s = one 128-row block of one sweep: s < nblk forward (L y = rhs, block i = s), s >= nblk backward
+// (U x = y, block i = 2*nblk-1-s).  A step is a left-looking dot-product form:
+//     acc = rhs_i - sum_{j solved before i} W(i,j) * sol_j ;   sol_i = inv(D_i) * acc
+// so a CTA streams the 128x128 fp32 tiles of its block row with 128-bit loads issued BEFORE it waits for sol_j, and
+// only the last tile + the 64 KiB inverse (prefetched into shared memory with cp.async) sit on the dependency chain.
+// Steps complete strictly in order; `ready` = number of completed steps is published with a release store and polled
+// with acquire loads.  CTA c owns steps c, c+G, ... in ascending order and the launch is cooperative (all CTAs are
+// co-resident), so every wait is on a step owned by a running CTA.  HBM-bound: 4*n^2 bytes per solve.
+constexpr int TSV_THREADS = 256;
 constexpr int DBS = kDiagBlock;
+constexpr int TSV_SMEM_BYTES = DBS * DBS * (int)sizeof(float);
 
-__global__ void __launch_bounds__(TS_THREADS)
-trsv_step_kernel(const float* __restrict__ W, long long ldw, const float* __restrict__ inv, int j0, int row_begin,
-                 int row_end, float* __restrict__ y, float* __restrict__ sol) {
-    __shared__ float ys[DBS];
-    __shared__ float part[2][DBS];
-    __shared__ float s[DBS];
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TSV_THREADS)
+lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
+                const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
+                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready) {
+    extern __shared__ __align__(16) float s_inv[];  // 128 x 128 inverse of the step's diagonal block
+    __shared__ __align__(16) float s_part[8][DBS];
+    __shared__ float s_acc[DBS];
     const int tid = threadIdx.x;
-    if (tid < DBS) ys[tid] = y[j0 + tid];
-    __syncthreads();
-    {
-        const int r = tid & (DBS - 1), half = tid >> 7;  // 2 threads per row of the inverse
-        const float* ip = inv + r + (long long)(half * 64) * DBS;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 64; ++c) acc = fmaf(__ldg(ip + (long long)c * DBS), ys[half * 64 + c], acc);
-        part[half][r] = acc;
-    }
-    __syncthreads();
-    if (tid < DBS) {
-        const float v = part[0][tid] + part[1][tid];
-        s[tid] = v;
-        if (blockIdx.x == 0) sol[j0 + tid] = v;
-    }
-    __syncthreads();
-    const int r = row_begin + blockIdx.x * TS_THREADS + tid;
-    if (r < row_end) {
-        const float* wp = W + r + (long long)j0 * ldw;
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < DBS; c += 2) {
-            acc0 = fmaf(__ldg(wp + (long long)c * ldw), s[c], acc0);
-            acc1 = fmaf(__ldg(wp + (long long)(c + 1) * ldw), s[c + 1], acc1);
+    const int rg = tid & 31, cg = tid >> 5;  // rows 4rg.., columns 16cg.. of a tile
+    unsigned seen = 0;
+    for (int s = blockIdx.x; s < 2 * nblk; s += gridDim.x) {
+        const bool back = s >= nblk;
+        const int t = back ? s - nblk : s;         // tiles in this block row
+        const int i = back ? nblk - 1 - t : t;     // block row
+        const float* solv = back ? xsol : ysol;
+        {   // prefetch the inverse (independent of every other step)
+            const float* inv = (back ? Uinv : Linv) + (long long)i * DBS * DBS;
+#pragma unroll
+            for (int u = 0; u < DBS * DBS / 4 / TSV_THREADS; ++u)
+                cp_async16(s_inv + 4 * (tid + u * TSV_THREADS), inv + 4 * (tid + u * TSV_THREADS));
         }
-        y[r] -= (acc0 + acc1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* wrow = W + (long long)i * DBS + 4 * rg;
+        for (int tt = 0; tt < t; ++tt) {
+            const int j = back ? nblk - 1 - tt : tt;
+            const float* wp = wrow + ((long long)j * DBS + 16 * cg) * ldw;
+            float4 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)q * ldw));
+            const unsigned need = (back ? nblk : 0) + tt + 1;
+            while (seen < need) seen = ld_acquire_u32(ready);
+            const float4* sp = reinterpret_cast<const float4*>(solv + j * DBS + 16 * cg);
+            float sv[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x4 = __ldcg(sp + q);
+                sv[4 * q] = x4.x; sv[4 * q + 1] = x4.y; sv[4 * q + 2] = x4.z; sv[4 * q + 3] = x4.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                acc.x = fmaf(v[q].x, sv[q], acc.x);
+                acc.y = fmaf(v[q].y, sv[q], acc.y);
+                acc.z = fmaf(v[q].z, sv[q], acc.z);
+                acc.w = fmaf(v[q].w, sv[q], acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = acc;
+        if (back) while (seen < (unsigned)nblk) seen = ld_acquire_u32(ready);  // y of this block row must be final
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < DBS) {
+            const int row = i * DBS + tid;
+            float a;
+            if (back) a = __ldcg(ysol + row);
+            else a = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) a -= s_part[g][tid];
+            s_acc[tid] = a;
+        }
+        __syncthreads();
+        {   // sol_i = inv * acc : 2 threads per row, 64 columns each
+            const int r = tid & (DBS - 1), h = tid >> 7;
+            const float* ip = s_inv + r + (h * 64) * DBS;
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < 64; c += 2) {
+                p0 = fmaf(ip[c * DBS], s_acc[h * 64 + c], p0);
+                p1 = fmaf(ip[(c + 1) * DBS], s_acc[h * 64 + c + 1], p1);
+            }
+            s_part[h][r] = p0 + p1;
+        }
+        __syncthreads();
+        if (tid < DBS) {
+            const float v = s_part[0][tid] + s_part[1][tid];
+            const int row = i * DBS + tid;
+            if (back) {
+                xsol[row] = v;
+                if (row < n) {
+                    if (d_out) d_out[row] = static_cast<double>(v);
+                    if (x_accum) x_accum[row] += static_cast<double>(v);
+                }
+            } else {
+                ysol[row] = v;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            st_release_u32(ready, (unsigned)(s + 1));
+        }
     }
 }
 
@@ -153,28 +218,29 @@ int launch_residual(const double* A, long long lda, int n, const double* x, cons
 }
 
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
-                    const double* rhs, float* y, double* d_out, double* x_accum, cudaStream_t st) {
-    float* sol = y + npad;  // caller provides 2*npad floats
-    to_float_kernel<<<(npad + 255) / 256, 256, 0, st>>>(rhs, y, n, npad);
-    const int nblk = npad / DBS;
-    for (int j = 0; j < nblk; ++j) {  // L y' = y
-        const int j0 = j * DBS;
-        const int rb = j0 + DBS, re = npad;
-        const int g = (re - rb + TS_THREADS - 1) / TS_THREADS;
-        trsv_step_kernel<<<g > 0 ? g : 1, TS_THREADS, 0, st>>>(W, ldw, Linv32 + (long long)j * DBS * DBS, j0, rb, re, y,
-                                                               sol);
+                    const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st) {
+    static int max_grid = 0;
+    if (!max_grid) {
+        cudaError_t e = cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSV_SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_solve_kernel, TSV_THREADS, TSV_SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+        max_grid = sms * per_sm;
     }
-    // sol now holds y' ; move it back into y for the backward sweep
-    cudaMemcpyAsync(y, sol, npad * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    for (int j = nblk - 1; j >= 0; --j) {  // U x = y'
-        const int j0 = j * DBS;
-        const int rb = 0, re = j0;
-        const int g = (re - rb + TS_THREADS - 1) / TS_THREADS;
-        trsv_step_kernel<<<g > 0 ? g : 1, TS_THREADS, 0, st>>>(W, ldw, Uinv32 + (long long)j * DBS * DBS, j0, rb, re, y,
-                                                               sol);
-    }
-    finish_solve_kernel<<<(n + 255) / 256, 256, 0, st>>>(sol, n, d_out, x_accum);
-    return (int)cudaGetLastError();
+    int nblk = npad / DBS;
+    float* ysol = y;
+    float* xsol = y + npad;  // caller provides 2*npad floats
+    cudaError_t e = cudaMemsetAsync(ready, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = nblk < max_grid ? nblk : max_grid;
+    void* args[] = {(void*)&W, (void*)&ldw, (void*)&n, (void*)&nblk, (void*)&Linv32, (void*)&Uinv32, (void*)&rhs,
+                    (void*)&ysol, (void*)&xsol, (void*)&d_out, (void*)&x_accum, (void*)&ready};
+    return (int)cudaLaunchCooperativeKernel((void*)lu_solve_kernel, dim3(grid), dim3(TSV_THREADS), args, TSV_SMEM_BYTES,
+                                            st);
 }
 
 }  // namespace mplu

@@ -33,8 +33,8 @@ int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, 
 int launch_residual(const double* A, long long lda, int n, const double* x, const double* b, double* r,
                     double* partial, int nchunk, double* norms, cudaStream_t st);
 // solve L U d = r with the fp32 factors in W (unit-lower L, U), blocked by kDiagBlock with the fp32 inverses of the
-// diagonal blocks; y (fp32 work vector of length npad).  d_out (fp64) = solution; if x_accum != null, x_accum += d.
+// diagonal blocks; y (fp32 work vectors, 2*npad floats); ready = one device word (step counter of the sweep).  d_out (fp64) = solution; if x_accum != null, x_accum += d.
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
-                    const double* rhs, float* y, double* d_out, double* x_accum, cudaStream_t st);
+                    const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st);
 
 }  // namespace mplu

@@ -36,6 +36,7 @@ struct mplu_context {
     double* anorm = nullptr;      // [0] ||A||inf, [1] ||b||inf
     double* rowsum_part = nullptr;
     int* status = nullptr;
+    unsigned* ready = nullptr;    // step counter of the cooperative triangular-solve kernel
     // refinement
     double* r = nullptr;
     double* partial = nullptr;
@@ -263,13 +264,12 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
     const int n = c->n, npad = c->npad;
     const long long ld = npad;
     cudaStream_t st = c->stream;
-    const int nblk = npad / kDiagBlock;
-    const int solve_launches = 2 * nblk + 3;
+    const int solve_launches = 1;
 
     CK(cudaMemsetAsync(c->anorm + 1, 0, sizeof(double), st));
     absmax_kernel<<<64, 256, 0, st>>>(db, n, c->anorm + 1);
     // first solve: x = (LU)^-1 b
-    CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, db, c->y, dx, nullptr, st));
+    CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, db, c->y, dx, nullptr, c->ready, st));
     c->kernel_launches += solve_launches + 1;
 
     double h_norms[2] = {0, 0}, h_an[2] = {0, 0};
@@ -291,7 +291,7 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
         if (!(h_norms[0] == h_norms[0])) break;  // NaN: give up
         if (h_norms[0] <= thresh) { converged = 1; break; }
         if (iters >= max_iters) break;
-        CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, c->r, c->y, nullptr, dx, st));
+        CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, c->r, c->y, nullptr, dx, c->ready, st));
         c->kernel_launches += solve_launches;
         ++iters;
     }
@@ -359,6 +359,7 @@ int mplu_create(mplu_context** out, int device) {
     CK(cudaMalloc(&c->anorm, 2 * sizeof(double)));
     CK(cudaMalloc(&c->norms, 2 * sizeof(double)));
     CK(cudaMalloc(&c->status, sizeof(int)));
+    CK(cudaMalloc(&c->ready, sizeof(unsigned)));
     *out = c;
     return 0;
 }
@@ -368,7 +369,7 @@ void mplu_destroy(mplu_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_work(c);
-    cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status);
+    cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status); cudaFree(c->ready);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
