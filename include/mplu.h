@@ -35,13 +35,16 @@ enum { MPLU_GEMM_AUTO = -1, MPLU_GEMM_CG1 = 0, MPLU_GEMM_CG2 = 1 };
 
 typedef struct mplu_options {
     int precision;    /* MPLU_FP16 (default) or MPLU_BF16: panel/operand storage type; accumulation is fp32 */
-    int nb;           /* outer (trailing-update) block size, multiple of 128; default 1024 */
+    int nb;           /* outer (trailing-update) block size, multiple of 128; 0 (default) = by n: 2048 / 1024 / 512 */
     int max_iters;    /* refinement iteration cap, default 30 (LAPACK dsgesv ITERMAX) */
     double tol;       /* <= 0: dsgesv rule ||r||_inf <= ||x||_inf ||A||_inf eps sqrt(n); else relative to ||A|| ||x|| */
     int gemm_variant; /* MPLU_GEMM_AUTO / CG1 (128x256 tiles) / CG2 (CTA-pair 256x256 tiles) */
     int max_sms;      /* 0 = all SMs */
     int a_exp;        /* fp16 only: A-type shadows are scaled so max|A| maps into (2^(a_exp-1), 2^a_exp]; default 11 */
     int l_exp;        /* fp16 only: multipliers are scaled by 2^l_exp; default 11 */
+    int lookahead;    /* 1 (default): factor panel k+1 on a second stream while the rest of update k runs */
+    int side_sms;     /* SMs reserved for the look-ahead panel stream (default 24) */
+    int use_graph;    /* 1 (default): capture the factorization schedule once per (n, options) into a CUDA graph */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -47,27 +47,30 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mt
     nt = r / gm;
 }
 
-// ---- epilogue helpers: one 32-column chunk of one row per thread.  kFull = the whole 32x32 patch is in range, so
-// the hot path carries no per-element predicates or branches (the first version of this epilogue was 13.7k SASS
-// instructions and instruction-fetch bound: profiles/r01_gemm_epilogue_v1.txt).
-template <bool kFull>
-__device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, int row, int col0) {
-    if (p.Cin64) {
-        const double* src = p.Cin64 + row + (long long)col0 * p.ldc64;
+// ---- epilogue helpers: one 32-column chunk of one row per thread, ONE call site each (software-pipelined chunk loop
+// below).  The first version of this epilogue was 13.7k SASS instructions and instruction-fetch bound; the second
+// kept the steady state compact but still carried 13.5k instructions of variants, so every small panel GEMM ran
+// 25-35 us on a cold instruction cache (gpurun_out/launches_r01b_n16384.csv).  kRagged = per-element bounds checks
+// (arbitrary M, N: the mplu_gemm16 hook); otherwise M % 32 == 0, N % 32 == 0, h_cols % 32 == 0 and a chunk is
+// either entirely inside the matrix or entirely outside (warp-uniform test, no per-element predicates).
+template <bool kRagged>
+__device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, int row, int col0, bool ok) {
+    const float* src = p.Cin + row + (long long)col0 * p.ldcin;
+    if constexpr (kRagged) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            dst[j] = (kFull || (row < p.M && col0 + j < p.N)) ? static_cast<float>(__ldg(src + (long long)j * p.ldc64)) : 0.f;
+        for (int j = 0; j < 32; ++j) dst[j] = (row < p.M && col0 + j < p.N) ? src[(long long)j * p.ldcin] : 0.f;
     } else {
-        const float* src = p.Cin + row + (long long)col0 * p.ldcin;
+        if (ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            dst[j] = (kFull || (row < p.M && col0 + j < p.N)) ? src[(long long)j * p.ldcin] : 0.f;
+            for (int j = 0; j < 32; ++j) dst[j] = src[(long long)j * p.ldcin];
+        }
     }
 }
 
-template <bool kFull>
+template <bool kRagged>
 __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (&cin)[32], const GemmParams& p,
-                                          float alpha, float hs, float hmax, int row, int wrow0, int col0, bool& ovf) {
+                                          float alpha, float hs, int row, int col0, bool ok, float& mx) {
+    if (!kRagged && !ok) return;
     float out[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) out[j] = fmaf(alpha, __uint_as_float(v[j]), cin[j]);
@@ -75,36 +78,34 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
         float* dst = p.C + row + (long long)col0 * p.ldc;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            if (kFull || (row < p.M && col0 + j < p.N)) dst[(long long)j * p.ldc] = out[j];
+            if (!kRagged || (row < p.M && col0 + j < p.N)) dst[(long long)j * p.ldc] = out[j];
     }
-    if (p.H && (wrow0 < p.h_rows || col0 < p.h_cols)) {  // warp-uniform reject of chunks outside the shadow region
+    if (p.H) {
+        // shadow region: every row of the columns < h_cols, and the rows < h_rows of every column
         const bool row_in = row < p.h_rows;
-        if (p.bf16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.H) + row + (long long)col0 * p.ldh;
+        if (kRagged || row_in || col0 < p.h_cols) {
+            if (p.bf16) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.H) + row + (long long)col0 * p.ldh;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float hv = out[j] * hs;
-                if ((kFull || (row < p.M && col0 + j < p.N)) && (row_in || col0 + j < p.h_cols))
-                    dst[(long long)j * p.ldh] = __float2bfloat16_rn(hv);
-            }
-        } else {
-            __half* dst = reinterpret_cast<__half*>(p.H) + row + (long long)col0 * p.ldh;
-            float mx = 0.f;
+                for (int j = 0; j < 32; ++j)
+                    if (!kRagged || (row < p.M && col0 + j < p.N && (row_in || col0 + j < p.h_cols)))
+                        dst[(long long)j * p.ldh] = __float2bfloat16_rn(out[j] * hs);
+            } else {
+                __half* dst = reinterpret_cast<__half*>(p.H) + row + (long long)col0 * p.ldh;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float hv = out[j] * hs;
-                if ((kFull || (row < p.M && col0 + j < p.N)) && (row_in || col0 + j < p.h_cols)) {
-                    dst[(long long)j * p.ldh] = __float2half_rn(hv);
-                    mx = fmaxf(mx, fabsf(hv));
-                    ovf |= (hv != hv);
+                for (int j = 0; j < 32; ++j) {
+                    const float hv = out[j] * hs;
+                    if (!kRagged || (row < p.M && col0 + j < p.N && (row_in || col0 + j < p.h_cols))) {
+                        dst[(long long)j * p.ldh] = __float2half_rn(hv);
+                        mx = fmaxf(mx, fabsf(hv));  // inf propagates; a NaN needs an inf operand, caught when it was made
+                    }
                 }
             }
-            ovf |= (mx > hmax);
         }
     }
 }
 
-template <int kCG, bool kAMN>
+template <int kCG, bool kAMN, bool kRagged>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using C = Cfg<kCG>;
@@ -236,73 +237,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ------------------------------------------------------------ epilogue warps 0..7
         // warp w: TMEM lanes 32*(w%4).. (rows), columns [128*(w/4), +128) of the tile in 4 chunks of 32.
-        // The addend C is software-prefetched one chunk ahead (also across tiles, i.e. while the MMAs of this
-        // tile are still running) so that each warp keeps 2 x 32 x 128 B of loads in flight.
+        // Software pipeline over the flat chunk sequence of all tiles of this CTA: iteration i issues the addend
+        // loads of chunk i (also across tiles, i.e. while the MMAs of that tile are still running) and then
+        // finishes chunk i-1, so each warp keeps 32 x 128 B of loads in flight behind its stores.
         float alpha = p.alpha;
         if (p.alpha_p1) alpha *= __ldg(p.alpha_p1);
         if (p.alpha_p2) alpha *= __ldg(p.alpha_p2);
         float hs = p.hscale;
         if (p.hscale_p) hs *= __ldg(p.hscale_p);
-        const float hmax = p.bf16 ? 3.0e38f : 65504.f;
         const uint32_t q = warp & 3, half = warp >> 2;
-        const bool has_cin = (p.Cin != nullptr) || (p.Cin64 != nullptr);
-        bool ovf = false;
+        const bool has_cin = (p.Cin != nullptr);
+        float mx = 0.f;
 
-        float cinA[32], cinB[32];
+        float cin_cur[32], cin_nxt[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { cinA[j] = 0.f; cinB[j] = 0.f; }
-        uint32_t iter = 0;
-        int t = first_tile;
-        int mt = 0, nt = 0;
-        if (t < num_tiles) {
-            tile_coords(t, num_m, num_n, mt, nt);
-            if (has_cin) {
-                const int wrow0 = mt * BM * kCG + cta_rank * BM + q * 32, c0 = nt * BN + half * 128;
-                if (wrow0 + 32 <= p.M && c0 + 32 <= p.N) epi_load<true>(cinA, p, wrow0 + lane, c0);
-                else epi_load<false>(cinA, p, wrow0 + lane, c0);
-            }
-        }
-        for (; t < num_tiles; t += tile_step, ++iter) {
-            const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-            const int wrow0 = mt * BM * kCG + cta_rank * BM + q * 32;
-            const int row = wrow0 + lane;
-            const int colbase = nt * BN + half * 128;
-            const bool full = (wrow0 + 32 <= p.M) && (colbase + 128 <= p.N);  // warp-uniform
-            // next tile (for the cross-tile prefetch)
-            const int tn = t + tile_step;
-            int mtn = 0, ntn = 0;
-            if (tn < num_tiles) tile_coords(tn, num_m, num_n, mtn, ntn);
-
-            ptx::mbar_wait(&tfull[as], aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BN + half * 128;
-            uint32_t v[32];
+        for (int j = 0; j < 32; ++j) { cin_cur[j] = 0.f; cin_nxt[j] = 0.f; }
+        const int my_tiles = first_tile < num_tiles ? (num_tiles - first_tile + tile_step - 1) / tile_step : 0;
+        const int nchunks = my_tiles * 4;
+        int t_row0 = 0, t_colbase = 0;              // tile of the chunk being loaded
+        int cur_row0 = 0, cur_col0 = 0;             // chunk being finished
+        bool cur_ok = false;
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 64) {
-                // chunk c (addend in cinA); prefetch chunk c+32 into cinB
-                ptx::tmem_ld_32x32(taddr + c, v);
-                if (has_cin) {
-                    if (full) epi_load<true>(cinB, p, row, colbase + c + 32);
-                    else epi_load<false>(cinB, p, row, colbase + c + 32);
+        for (int i = 0; i <= nchunks; ++i) {
+            int nx_col0 = 0;
+            bool nx_ok = false;
+            if (i < nchunks) {
+                if ((i & 3) == 0) {
+                    int mt, nt;
+                    tile_coords(first_tile + (i >> 2) * tile_step, num_m, num_n, mt, nt);
+                    t_row0 = mt * BM * kCG + cta_rank * BM + q * 32;
+                    t_colbase = nt * BN + half * 128;
                 }
-                ptx::tmem_ld_wait();
-                if (full) epi_store<true>(v, cinA, p, alpha, hs, hmax, row, wrow0, colbase + c, ovf);
-                else epi_store<false>(v, cinA, p, alpha, hs, hmax, row, wrow0, colbase + c, ovf);
-                // chunk c+32 (cinB); prefetch chunk c+64 -- or the next tile's first chunk -- into cinA
-                ptx::tmem_ld_32x32(taddr + c + 32, v);
-                if (has_cin) {
-                    if (c == 0) {
-                        if (full) epi_load<true>(cinA, p, row, colbase + 64);
-                        else epi_load<false>(cinA, p, row, colbase + 64);
-                    } else if (tn < num_tiles) {
-                        const int wrow0n = mtn * BM * kCG + cta_rank * BM + q * 32, c0n = ntn * BN + half * 128;
-                        if (wrow0n + 32 <= p.M && c0n + 32 <= p.N) epi_load<true>(cinA, p, wrow0n + lane, c0n);
-                        else epi_load<false>(cinA, p, wrow0n + lane, c0n);
-                    }
+                nx_col0 = t_colbase + (i & 3) * 32;
+                nx_ok = (t_row0 < p.M) && (nx_col0 < p.N);
+            }
+            uint32_t v[32];
+            if (i > 0) {
+                const uint32_t c = (i - 1) & 3, it = (i - 1) >> 2;
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                if (c == 0) {
+                    ptx::mbar_wait(&tfull[as], aphase);
+                    ptx::tc_fence_after();
                 }
+                ptx::tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + as * BN + half * 128 + c * 32, v);
+            }
+            if (i < nchunks && has_cin) epi_load<kRagged>(cin_nxt, p, t_row0 + lane, nx_col0, nx_ok);
+            if (i > 0) {
                 ptx::tmem_ld_wait();
-                if (c == 64) {
+                if (((i - 1) & 3) == 3) {
                     // accumulator fully read: hand the TMEM stage back before the last stores
+                    const uint32_t as = ((i - 1) >> 2) & 1;
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -310,12 +294,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else ptx::mbar_arrive_cluster(&tempty[as], 0);
                     }
                 }
-                if (full) epi_store<true>(v, cinB, p, alpha, hs, hmax, row, wrow0, colbase + c + 32, ovf);
-                else epi_store<false>(v, cinB, p, alpha, hs, hmax, row, wrow0, colbase + c + 32, ovf);
+                epi_store<kRagged>(v, cin_cur, p, alpha, hs, cur_row0 + lane, cur_col0, cur_ok, mx);
             }
-            mt = mtn; nt = ntn;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cin_cur[j] = cin_nxt[j];
+            cur_row0 = t_row0; cur_col0 = nx_col0; cur_ok = nx_ok;
         }
-        if (p.status && __any_sync(0xffffffffu, ovf) && lane == 0) atomicOr(p.status, 1);
+        const float hmax = p.bf16 ? 3.0e38f : 65504.f;
+        if (p.status && __any_sync(0xffffffffu, mx > hmax) && lane == 0) atomicOr(p.status, 1);
     }
 
     // ---------------------------------------------------------------- teardown
@@ -341,17 +327,11 @@ EncodeFn get_encode_fn() {
     return fn;
 }
 
-template <int kCG, bool kAMN>
+template <int kCG, bool kAMN, bool kRagged>
 int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
                    cudaStream_t stream) {
     using C = Cfg<kCG>;
-    auto kern = gemm_tc_kernel<kCG, kAMN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    auto kern = gemm_tc_kernel<kCG, kAMN, kRagged>;
     const int num_m = (p.M + BM * kCG - 1) / (BM * kCG);
     const int num_n = (p.N + BN - 1) / BN;
     long long want = (long long)num_m * num_n * kCG;
@@ -374,7 +354,26 @@ int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmPar
     return (int)cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, p);
 }
 
+template <int kCG, bool kAMN, bool kRagged>
+int set_smem_attr() {
+    return (int)cudaFuncSetAttribute(gemm_tc_kernel<kCG, kAMN, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<kCG>::SMEM_BYTES);
+}
+
 }  // namespace
+
+int gemm_tc_init() {
+    int rc = 0;
+    if ((rc = set_smem_attr<1, true, false>())) return rc;
+    if ((rc = set_smem_attr<2, true, false>())) return rc;
+    if ((rc = set_smem_attr<1, false, false>())) return rc;
+    if ((rc = set_smem_attr<2, false, false>())) return rc;
+    if ((rc = set_smem_attr<1, true, true>())) return rc;
+    if ((rc = set_smem_attr<2, true, true>())) return rc;
+    if ((rc = set_smem_attr<1, false, true>())) return rc;
+    if ((rc = set_smem_attr<2, false, true>())) return rc;
+    return get_encode_fn() ? 0 : -1;
+}
 
 int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                     uint32_t box_cols) {
@@ -413,11 +412,22 @@ int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, 
         }
         max_sms = sms;
     }
+    // aligned fast path: whole 32 x 32 epilogue chunks (the factorization only ever issues these)
+    const bool ragged = (p.M % 32) || (p.N % 32) || (p.H && (p.h_cols % 32) && p.h_cols < p.N);
+    if (!ragged) {
+        switch (variant) {
+            case GEMM_CG1_AMN: return launch_variant<1, true, false>(tmA, tmB, p, max_sms, stream);
+            case GEMM_CG2_AMN: return launch_variant<2, true, false>(tmA, tmB, p, max_sms, stream);
+            case GEMM_CG1_AK: return launch_variant<1, false, false>(tmA, tmB, p, max_sms, stream);
+            case GEMM_CG2_AK: return launch_variant<2, false, false>(tmA, tmB, p, max_sms, stream);
+            default: return (int)cudaErrorInvalidValue;
+        }
+    }
     switch (variant) {
-        case GEMM_CG1_AMN: return launch_variant<1, true>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG2_AMN: return launch_variant<2, true>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG1_AK: return launch_variant<1, false>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG2_AK: return launch_variant<2, false>(tmA, tmB, p, max_sms, stream);
+        case GEMM_CG1_AMN: return launch_variant<1, true, true>(tmA, tmB, p, max_sms, stream);
+        case GEMM_CG2_AMN: return launch_variant<2, true, true>(tmA, tmB, p, max_sms, stream);
+        case GEMM_CG1_AK: return launch_variant<1, false, true>(tmA, tmB, p, max_sms, stream);
+        case GEMM_CG2_AK: return launch_variant<2, false, true>(tmA, tmB, p, max_sms, stream);
         default: return (int)cudaErrorInvalidValue;
     }
 }

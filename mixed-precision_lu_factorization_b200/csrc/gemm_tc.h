@@ -28,8 +28,6 @@ struct GemmParams {
     long long ldc;
     const float* Cin;  // fp32 addend (may alias C; null = none)
     long long ldcin;
-    const double* Cin64;  // fp64 addend used instead of Cin on an element's first touch (null = none)
-    long long ldc64;
     void* H;  // optional 16-bit shadow of the output, column-major, offset to the block origin
     long long ldh;
     int h_rows, h_cols;     // shadow is written where (m < h_rows || n < h_cols)
@@ -50,6 +48,9 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 // Box shapes each variant expects for its A and B maps.
 void gemm_box_shapes(int variant, uint32_t* a_box_rows, uint32_t* a_box_cols, uint32_t* b_box_rows,
                      uint32_t* b_box_cols);
+
+// Opt every kernel instantiation into its dynamic shared-memory size (once per device, before any launch / capture).
+int gemm_tc_init();
 
 // Launch on `stream` using at most `max_sms` SMs (0 = all).  Returns cudaError_t as int.
 int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,

@@ -19,6 +19,7 @@ enum ScaleIdx : int {
 constexpr int kDiagBlock = 128;  // diagonal block / base panel width
 
 // panel.cu
+int panel_init();  // per-device kernel attributes; call before the first launch / graph capture
 int launch_first_touch(const double* A, long long lda, int n, float* W, long long ldw, int npad, float* amax,
                        double* rowsum_part, int nchunk, double* anorm, cudaStream_t st);
 int launch_scales(const float* amax, float* scales, int target_exp_a, int exp_l, int bf16, cudaStream_t st);

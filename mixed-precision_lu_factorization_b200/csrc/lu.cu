@@ -1,8 +1,13 @@
 // Host orchestration of the blocked right-looking no-pivot LU + fp64 iterative refinement, and the C ABI of
 // include/mplu.h.  This is the B200-native counterpart of the panel loop in /root/reference/MPF.cu:100-241:
 //   reference per panel (r = 32):  gather -> fp16 pivot search -> LASWP -> fp64 panel LU -> Dtrsm -> rank-32 Dgemm
-//   here per outer block (nb = 1024): 128-wide sub-panels [diag_lu -> L21 = A21*inv(U11) -> U12 = inv(L11)*A12 ->
-//   in-panel Schur], then one rank-nb tcgen05 trailing update; all operands 16-bit shadows, accumulation fp32.
+//   here per outer block (nb = 2048): the tall panel is factored RECURSIVELY (halving down to 128-wide leaves:
+//   diag_lu + L21 = A21*inv(U11) on the tensor cores), the block row by a recursive TRSM whose leaves multiply with
+//   the explicit 128x128 inverses, then one rank-nb tcgen05 trailing update; operands are 16-bit shadows,
+//   accumulation and the working matrix are fp32.
+// Look-ahead: the trailing update of step k is split into the next panel's columns (done first) and the rest; the
+// next panel is factored on a second stream restricted to `side_sms` SMs while the rest of the update runs on the
+// others.  The whole schedule is captured once into a CUDA graph per (n, options) and replayed.
 // No host<->device round trips inside the loop (the reference does one per panel, MPF.cu:146,158).
 #include "../../include/mplu.h"
 #include "gemm_tc.h"
@@ -49,6 +54,15 @@ struct mplu_context {
     // tensor maps
     CUtensorMap tmWh_A, tmWh_B1, tmWh_B2, tmLinv_A, tmUinv_B1, tmUinv_B2;
     int gemm_launches = 0, kernel_launches = 0;
+    // look-ahead / graph
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp; const void* W; } gkey{};
+    int g_gemm_launches = 0, g_kernel_launches = 0, g_trail_count = 0;
+    double g_trail_flops = 0, g_trail_bytes = 0;
+    bool capturing = false;
+    int num_sms = 0;
     // per-launch timing of the trailing updates (events are cheap: <= npad/nb pairs per factorization)
     static constexpr int kMaxTrail = 1024;
     cudaEvent_t trail_ev[2 * kMaxTrail] = {};
@@ -70,6 +84,7 @@ namespace {
     } while (0)
 
 void free_work(mplu_context* c) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     cudaFree(c->W); cudaFree(c->Wh); cudaFree(c->Linv16); cudaFree(c->Uinv16); cudaFree(c->Linv32); cudaFree(c->Uinv32);
     cudaFree(c->inv_scales); cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
     c->W = nullptr; c->Wh = nullptr; c->Linv16 = c->Uinv16 = nullptr; c->Linv32 = c->Uinv32 = nullptr;
@@ -108,6 +123,10 @@ int ensure_work(mplu_context* c, int n) {
     return 0;
 }
 
+void resolve_options(mplu_context* c, int n) {
+    if (c->opts.nb <= 0) c->opts.nb = n >= 12288 ? 2048 : (n >= 4096 ? 1024 : 512);
+}
+
 struct GemmCall {
     // A operand: 0 = Wh block, 1 = Linv16 block ; B operand: 0 = Wh block, 1 = Uinv16 block
     int a_kind, a_r0, a_c0;
@@ -121,11 +140,16 @@ struct GemmCall {
     int h_rows, h_cols;
 };
 
-int run_gemm(mplu_context* c, const GemmCall& g) {
+// Where a piece of the schedule runs: stream + SM budget (0 = all SMs).
+struct Lane {
+    cudaStream_t st;
+    int sms;
+};
+
+int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     int variant;
     if (c->opts.gemm_variant == MPLU_GEMM_CG1) variant = GEMM_CG1_AMN;
-    else if (c->opts.gemm_variant == MPLU_GEMM_CG2) variant = (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
     else variant = (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
     const bool cg2 = (variant == GEMM_CG2_AMN);
     const CUtensorMap* tmA = g.a_kind == 0 ? &c->tmWh_A : &c->tmLinv_A;
@@ -138,7 +162,6 @@ int run_gemm(mplu_context* c, const GemmCall& g) {
     p.ldc = ld;
     p.Cin = g.accumulate ? p.C : nullptr;
     p.ldcin = ld;
-    p.Cin64 = nullptr; p.ldc64 = 0;
     p.H = c->Wh + g.out_r0 + (long long)g.out_c0 * ld;
     p.ldh = ld;
     p.h_rows = g.h_rows; p.h_cols = g.h_cols;
@@ -148,97 +171,172 @@ int run_gemm(mplu_context* c, const GemmCall& g) {
     p.status = c->status;
     c->gemm_launches++;
     c->kernel_launches++;
-    return launch_gemm_tc(variant, tmA, tmB, p, c->opts.max_sms, c->stream);
+    int sms = ln.sms > 0 ? ln.sms : c->num_sms;
+    if (c->opts.max_sms > 0 && c->opts.max_sms < sms) sms = c->opts.max_sms;
+    return launch_gemm_tc(variant, tmA, tmB, p, sms, ln.st);
 }
 
-int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
-    CKI(ensure_work(c, n));
+inline int split_width(int w) { return kDiagBlock * ((w / kDiagBlock + 1) / 2); }
+
+// A[r0:r1, c0:c1) -= L[r0:r1, k0:k1) * U[k0:k1, c0:c1)   (Schur update; the result is A-type, shadow where asked)
+int schur_update(mplu_context* c, const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows,
+                 int h_cols) {
+    GemmCall g{0, r0, k0, 0, k0, c0, r1 - r0, c1 - c0, k1 - k0, r0, c0, true,
+               c->scales + SC_NEG_LA_INV, nullptr, c->scales + SC_A, h_rows, h_cols};
+    return run_gemm(c, ln, g);
+}
+
+// U[c0:c0+w, n0:n1) = inv(L11[c0:c0+w)) * A[c0:c0+w, n0:n1), in place; recursive, 128-wide leaves multiply with the
+// explicit inverse of the diagonal block (replaces cublasDtrsm, MPF.cu:215-225).
+int trsm_rec(mplu_context* c, const Lane& ln, int c0, int w, int n0, int n1) {
+    if (n1 <= n0) return 0;
+    if (w <= kDiagBlock) {
+        const int blk = c0 / kDiagBlock;
+        GemmCall t{1, 0, blk * kDiagBlock, 0, c0, n0, kDiagBlock, n1 - n0, kDiagBlock, c0, n0, false,
+                   c->inv_scales + 4 * blk + 1, c->scales + SC_A_INV, c->scales + SC_A, kDiagBlock, n1 - n0};
+        return run_gemm(c, ln, t);
+    }
+    const int h = split_width(w);
+    CKI(trsm_rec(c, ln, c0, h, n0, n1));
+    CKI(schur_update(c, ln, c0 + h, c0 + w, n0, n1, c0, c0 + h, w - h, n1 - n0));
+    return trsm_rec(c, ln, c0 + h, w - h, n0, n1);
+}
+
+// LU of the tall panel: columns [c0, c0+w), rows [c0, npad); recursive halving down to one diagonal block.
+int panel_rec(mplu_context* c, const Lane& ln, int c0, int w) {
+    const int npad = c->npad;
+    if (w <= kDiagBlock) {
+        const int blk = c0 / kDiagBlock;
+        CKI(launch_diag_lu(c->W, npad, c0, c->Linv16, c->Uinv16, c->Linv32, c->Uinv32, c->inv_scales, blk,
+                           c->opts.precision == MPLU_BF16, c->status, ln.st));
+        c->kernel_launches++;
+        const int below = c0 + kDiagBlock;
+        if (npad > below) {  // L21 = A21 * inv(U11), in place
+            GemmCall g{0, below, c0, 1, 0, blk * kDiagBlock, npad - below, kDiagBlock, kDiagBlock, below, c0, false,
+                       c->scales + SC_A_INV, c->inv_scales + 4 * blk + 3, c->scales + SC_L, npad - below, kDiagBlock};
+            CKI(run_gemm(c, ln, g));
+        }
+        return 0;
+    }
+    const int h = split_width(w);
+    CKI(panel_rec(c, ln, c0, h));
+    CKI(trsm_rec(c, ln, c0, h, c0 + h, c0 + w));
+    CKI(schur_update(c, ln, c0 + h, npad, c0 + h, c0 + w, c0, c0 + h, npad - c0 - h, w - h));
+    return panel_rec(c, ln, c0 + h, w - h);
+}
+
+int record_event(mplu_context* c, cudaEvent_t ev, cudaStream_t st) {
+    return (int)cudaEventRecordWithFlags(ev, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
+// Everything after the first touch: scales, shadows of the first block column / block row, the panel loop.
+int enqueue_factorization(mplu_context* c) {
     const int npad = c->npad;
     const long long ld = npad;
     const int bf16 = c->opts.precision == MPLU_BF16;
     int NB = c->opts.nb;
     if (NB < kDiagBlock) NB = kDiagBlock;
     NB = (NB / kDiagBlock) * kDiagBlock;
+    if (NB > npad) NB = npad;
     cudaStream_t st = c->stream;
-    c->gemm_launches = 0;
-    c->kernel_launches = 0;
-    c->trail_count = 0;
-    c->trail_flops = c->trail_bytes = 0;
-    CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
+    int side_sms = c->opts.side_sms > 0 ? c->opts.side_sms : 24;
+    side_sms -= side_sms % 2;
+    const bool lookahead = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16;
+    const Lane all{st, 0};
+    const Lane main_part{st, c->num_sms - side_sms};
+    const Lane side{c->side, side_sms};
 
-    CKI(launch_first_touch(dA, lda, n, c->W, ld, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
     CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+    if (npad > NB)
+        CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
+                               c->scales + SC_A, bf16, c->status, st));
     c->kernel_launches += 3;
-    // shadows of the first block column and block row
-    {
-        const int w = NB < npad ? NB : npad;
-        CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, w, c->scales + SC_A, bf16, c->status, st));
-        if (npad > w)
-            CKI(launch_shadow_cast(c->W + (long long)w * ld, ld, c->Wh + (long long)w * ld, ld, w, npad - w,
-                                   c->scales + SC_A, bf16, c->status, st));
-        c->kernel_launches += 2;
-    }
 
-    const float* sA = c->scales + SC_A;
-    const float* sAinv = c->scales + SC_A_INV;
-    const float* sL = c->scales + SC_L;
-    const float* sNeg = c->scales + SC_NEG_LA_INV;
-
+    CKI(panel_rec(c, all, 0, NB));
     for (int k = 0; k < npad; k += NB) {
         const int nbk = (NB < npad - k) ? NB : (npad - k);
-        const int kend = k + nbk;  // first column after the panel
-        for (int j = 0; j < nbk; j += kDiagBlock) {
-            const int cc = k + j;
-            const int blk = cc / kDiagBlock;
-            const int below = cc + kDiagBlock;
-            CKI(launch_diag_lu(c->W, ld, cc, c->Linv16, c->Uinv16, c->Linv32, c->Uinv32, c->inv_scales, blk, bf16,
-                               c->status, st));
-            c->kernel_launches++;
-            const float* sLinv_inv = c->inv_scales + 4 * blk + 1;
-            const float* sUinv_inv = c->inv_scales + 4 * blk + 3;
-            const int M1 = npad - below;
-            if (M1 > 0) {
-                // L21 = A21 * inv(U11)   (rows below the diagonal block, in place)
-                GemmCall g{0, below, cc, 1, 0, blk * kDiagBlock, M1, kDiagBlock, kDiagBlock, below, cc,
-                           false, sAinv, sUinv_inv, sL, M1, kDiagBlock};
-                CKI(run_gemm(c, g));
-                // pending updates of this block row right of the panel: A12 -= L[cc.., k..cc) * U[k..cc, kend..)
-                if (j > 0 && npad > kend) {
-                    GemmCall u{0, cc, k, 0, k, kend, kDiagBlock, npad - kend, j, cc, kend,
-                               true, sNeg, nullptr, sA, kDiagBlock, npad - kend};
-                    CKI(run_gemm(c, u));
-                }
-                // U12 = inv(L11) * A12   (block row right of the diagonal block, in place)
-                GemmCall t{1, 0, blk * kDiagBlock, 0, cc, below, kDiagBlock, M1, kDiagBlock, cc, below,
-                           false, sLinv_inv, sAinv, sA, kDiagBlock, M1};
-                CKI(run_gemm(c, t));
-                // Schur update inside the panel
-                const int Np = kend - below;
-                if (Np > 0) {
-                    GemmCall s{0, below, cc, 0, cc, below, M1, Np, kDiagBlock, below, below,
-                               true, sNeg, nullptr, sA, kDiagBlock, kDiagBlock};
-                    CKI(run_gemm(c, s));
-                }
-            }
+        const int kend = k + nbk;
+        if (kend >= npad) break;
+        const int nbn = (NB < npad - kend) ? NB : (npad - kend);
+        const int cnext = kend + nbn;  // end of the next panel's columns
+        // next panel's columns first: block row of U, then their Schur update (full shadow: the panel consumes it)
+        CKI(trsm_rec(c, all, k, nbk, kend, cnext));
+        CKI(schur_update(c, all, kend, npad, kend, cnext, k, kend, npad - kend, nbn));
+        const bool rest = cnext < npad;
+        const bool fork = lookahead && rest;
+        if (fork) {
+            CK(cudaEventRecord(c->ev_fork, st));
+            CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            CKI(panel_rec(c, side, kend, nbn));
+            CK(cudaEventRecord(c->ev_join, c->side));
         }
-        // trailing update A22 -= L21 * U12 with K = nbk
-        const int Mt = npad - kend;
-        if (Mt > 0) {
-            GemmCall s{0, kend, k, 0, k, kend, Mt, Mt, nbk, kend, kend, true, sNeg, nullptr, sA, NB, NB};
+        if (rest) {
+            const Lane& ln = fork ? main_part : all;
+            CKI(trsm_rec(c, ln, k, nbk, cnext, npad));
+            const int Mt = npad - kend, Nt = npad - cnext;
             const bool timed = c->trail_count < mplu_context::kMaxTrail;
             if (timed) {
                 cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
                 if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
-                CK(cudaEventRecord(e0, st));
+                CKI(record_event(c, e0, st));
             }
-            CKI(run_gemm(c, s));
+            // the rest of the trailing matrix: shadow only for the next panel's block row (its TRSM input)
+            CKI(schur_update(c, ln, kend, npad, cnext, npad, k, kend, nbn, 0));
             if (timed) {
-                CK(cudaEventRecord(c->trail_ev[2 * c->trail_count + 1], st));
+                CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], st));
                 c->trail_count++;
-                c->trail_flops += 2.0 * Mt * (double)Mt * nbk;
-                c->trail_bytes += 8.0 * Mt * (double)Mt;
+                c->trail_flops += 2.0 * Mt * (double)Nt * nbk;
+                c->trail_bytes += 8.0 * Mt * (double)Nt;
             }
         }
+        if (fork) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        else CKI(panel_rec(c, all, kend, nbn));
+    }
+    return 0;
+}
+
+int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
+    CKI(ensure_work(c, n));
+    const int npad = c->npad;
+    cudaStream_t st = c->stream;
+    CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
+    CKI(launch_first_touch(dA, lda, n, c->W, npad, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
+
+    const bool use_graph = c->opts.use_graph != 0;
+    mplu_context::GraphKey key{n, npad, c->opts.nb, c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
+                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->W};
+    const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
+    if (!hit) {
+        c->gemm_launches = 0;
+        c->kernel_launches = 2;  // first touch + anorm
+        c->trail_count = 0;
+        c->trail_flops = c->trail_bytes = 0;
+        if (use_graph) {
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            c->capturing = true;
+            int rc = enqueue_factorization(c);
+            c->capturing = false;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return (int)e;
+            e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { c->graph_exec = nullptr; return (int)e; }
+            memset(&c->gkey, 0, sizeof(c->gkey));
+            c->gkey = key;
+            c->g_gemm_launches = c->gemm_launches; c->g_kernel_launches = c->kernel_launches;
+            c->g_trail_count = c->trail_count; c->g_trail_flops = c->trail_flops; c->g_trail_bytes = c->trail_bytes;
+        } else {
+            CKI(enqueue_factorization(c));
+        }
+    }
+    if (use_graph) {
+        c->gemm_launches = c->g_gemm_launches; c->kernel_launches = c->g_kernel_launches;
+        c->trail_count = c->g_trail_count; c->trail_flops = c->g_trail_flops; c->trail_bytes = c->g_trail_bytes;
+        CK(cudaGraphLaunch(c->graph_exec, st));
     }
     c->factored = true;
     return 0;
@@ -333,13 +431,16 @@ extern "C" {
 void mplu_default_options(mplu_options* o) {
     if (!o) return;
     o->precision = MPLU_FP16;
-    o->nb = 1024;
+    o->nb = 0;  // auto: 2048 for n >= 12288, 1024 for n >= 4096, else 512
     o->max_iters = 30;
     o->tol = 0.0;
     o->gemm_variant = MPLU_GEMM_AUTO;
     o->max_sms = 0;
     o->a_exp = 11;
     o->l_exp = 11;
+    o->lookahead = 1;
+    o->side_sms = 24;
+    o->use_graph = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -352,7 +453,13 @@ int mplu_create(mplu_context** out, int device) {
     if (!c) return MPLU_E_ARG;
     c->device = device;
     mplu_default_options(&c->opts);
+    CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+    if (gemm_tc_init() != 0) return MPLU_E_TMAP;
+    CKI(panel_init());
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     CK(cudaMalloc(&c->scales, SC_COUNT * sizeof(float)));
     CK(cudaMalloc(&c->amax, sizeof(float)));
@@ -373,6 +480,10 @@ void mplu_destroy(mplu_context* c) {
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -383,6 +494,7 @@ int mplu_factor_device(mplu_context* c, int n, const double* dA, long long lda, 
     if (!c || !dA || n <= 0 || lda < n) return MPLU_E_ARG;
     CK(cudaSetDevice(c->device));
     if (opts) c->opts = *opts;
+    resolve_options(c, n);
     c->factored = false;
     return factor_impl(c, n, dA, lda);
 }
@@ -400,6 +512,7 @@ int mplu_gesv_device(mplu_context* c, int n, const double* dA, long long lda, co
     if (!c || !dA || !db || !dx || n <= 0 || lda < n) return MPLU_E_ARG;
     CK(cudaSetDevice(c->device));
     if (opts) c->opts = *opts;
+    resolve_options(c, n);
     if (stats) memset(stats, 0, sizeof(*stats));
     c->factored = false;
     CK(cudaEventRecord(c->ev[0], c->stream));
@@ -486,6 +599,7 @@ int mplu_gemm16(int variant, int bf16, int M, int N, int K, float alpha, const v
                 float hscale, int max_sms, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || !dA || !dB) return MPLU_E_ARG;
     if (beta != 0.f && beta != 1.f) return MPLU_E_ARG;
+    if (gemm_tc_init() != 0) return MPLU_E_TMAP;
     uint32_t abr, abc, bbr, bbc;
     gemm_box_shapes(variant, &abr, &abc, &bbr, &bbc);
     const bool amn = (variant == GEMM_CG1_AMN || variant == GEMM_CG2_AMN);
@@ -504,6 +618,7 @@ int mplu_gemm16(int variant, int bf16, int M, int N, int K, float alpha, const v
 
 int mplu_diag_lu128(float* dW, long long ldw, float* dLinv, float* dUinv, void* stream) {
     if (!dW || !dLinv || !dUinv) return MPLU_E_ARG;
+    CKI(panel_init());
     uint16_t* tmp16 = nullptr;
     float* sc = nullptr;
     CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
