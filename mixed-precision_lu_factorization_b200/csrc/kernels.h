@@ -27,7 +27,8 @@ int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, in
                        int bf16, int* status, cudaStream_t st);
 // inv_scales[4*blk + {0,1,2,3}] = {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv}
 int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, float* Linv32, float* Uinv32,
-                   float* inv_scales, int blk, int bf16, int* status, cudaStream_t st);
+                   float* inv_scales, int blk, int bf16, int* status, cudaStream_t st,
+                   long long* dbg_clk = nullptr);  // dbg_clk: optional device array of phase time stamps (clock64)
 
 // ir.cu
 // r = b - A*x (fp64), ||r||_inf and ||x||_inf into norms[0], norms[1]

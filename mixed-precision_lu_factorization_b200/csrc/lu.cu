@@ -630,6 +630,22 @@ int mplu_diag_lu128(float* dW, long long ldw, float* dLinv, float* dUinv, void* 
     return rc;
 }
 
+// development aid: same as mplu_diag_lu128 with clock64() stamps of the kernel's phases written to d_clocks[0..31]
+int mplu_diag_lu128_timed(float* dW, long long ldw, float* dLinv, float* dUinv, long long* d_clocks, void* stream) {
+    if (!dW || !dLinv || !dUinv) return MPLU_E_ARG;
+    CKI(panel_init());
+    uint16_t* tmp16 = nullptr;
+    float* sc = nullptr;
+    CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
+    CK(cudaMalloc(&sc, 4 * sizeof(float)));
+    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, dLinv, dUinv, sc, 0, 0, nullptr, (cudaStream_t)stream,
+                            d_clocks);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(tmp16);
+    cudaFree(sc);
+    return rc;
+}
+
 int mplu_residual(int n, const double* dA, long long lda, const double* dx, const double* db, double* dr,
                   double* dnorms, void* stream) {
     if (n <= 0 || !dA || !dx || !db || !dr || !dnorms) return MPLU_E_ARG;
