@@ -107,7 +107,12 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
 
 template <int kCG, bool kAMN, bool kRagged>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ GemmParams p0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p1) {
+    // Up to two independent problems share one launch ("grouped"): tiles [0, tiles0) belong to problem 0, the rest to
+    // problem 1 (p1.M == 0: none).  The panel code pairs the L-side and U-side products of one recursion node, which
+    // halves the number of dependent launches on the factorization's critical path.
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -125,10 +130,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t lane = threadIdx.x & 31;
     uint32_t cta_rank = 0;
     if constexpr (kCG == 2) cta_rank = ptx::cluster_ctarank();
+    ptx::griddep_launch();  // the stream successor may start its prologue now (it blocks in its own griddep_wait)
 
     if (warp == EPI_WARPS && lane == 0) {
-        ptx::prefetch_tmap(&tmA);
-        ptx::prefetch_tmap(&tmB);
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmB0);
+        if (p1.M > 0) {
+            ptx::prefetch_tmap(&tmA1);
+            ptx::prefetch_tmap(&tmB1);
+        }
         for (int i = 0; i < C::STAGES; ++i) {
             ptx::mbar_init(&full[i], kCG);  // one producer arrival per CTA of the pair (leader's barrier is used)
             ptx::mbar_init(&empty[i], 1);   // one tcgen05.commit
@@ -145,11 +155,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (kCG == 2) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // nothing above touched global memory: with a programmatic launch the prologue overlapped the predecessor
+    ptx::griddep_wait();
 
-    const int num_m = (p.M + BM * kCG - 1) / (BM * kCG);
-    const int num_n = (p.N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
-    const int num_kb = p.K / BK;
+    const int num_m0 = (p0.M + BM * kCG - 1) / (BM * kCG), num_n0 = (p0.N + BN - 1) / BN;
+    const int num_m1 = (p1.M + BM * kCG - 1) / (BM * kCG), num_n1 = (p1.N + BN - 1) / BN;
+    const int tiles0 = num_m0 * num_n0;
+    const int num_tiles = tiles0 + (p1.M > 0 ? num_m1 * num_n1 : 0);
     const int first_tile = blockIdx.x / kCG;
     const int tile_step = gridDim.x / kCG;
 
@@ -158,10 +170,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = first_tile; t < num_tiles; t += tile_step) {
+                const bool second = t >= tiles0;
+                const GemmParams& p = second ? p1 : p0;
+                const CUtensorMap& tmA = second ? tmA1 : tmA0;
+                const CUtensorMap& tmB = second ? tmB1 : tmB0;
                 int mt, nt;
-                tile_coords(t, num_m, num_n, mt, nt);
+                if (second) tile_coords(t - tiles0, num_m1, num_n1, mt, nt); else tile_coords(t, num_m0, num_n0, mt, nt);
                 const int m0 = mt * BM * kCG + cta_rank * BM;
                 const int n0 = nt * BN + cta_rank * C::LOAD_BN;
+                const int num_kb = p.K / BK;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     if constexpr (kCG == 1) {
@@ -198,9 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
         if (cta_rank == 0) {
-            const uint32_t idesc = make_idesc_f16(BM * kCG, BN, p.bf16 != 0, kAMN, false);
+            const uint32_t idesc = make_idesc_f16(BM * kCG, BN, p0.bf16 != 0, kAMN, false);
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int t = first_tile; t < num_tiles; t += tile_step, ++iter) {
+                const int num_kb = (t >= tiles0 ? p1.K : p0.K) / BK;
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
@@ -240,13 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Software pipeline over the flat chunk sequence of all tiles of this CTA: iteration i issues the addend
         // loads of chunk i (also across tiles, i.e. while the MMAs of that tile are still running) and then
         // finishes chunk i-1, so each warp keeps 32 x 128 B of loads in flight behind its stores.
-        float alpha = p.alpha;
-        if (p.alpha_p1) alpha *= __ldg(p.alpha_p1);
-        if (p.alpha_p2) alpha *= __ldg(p.alpha_p2);
-        float hs = p.hscale;
-        if (p.hscale_p) hs *= __ldg(p.hscale_p);
         const uint32_t q = warp & 3, half = warp >> 2;
-        const bool has_cin = (p.Cin != nullptr);
         float mx = 0.f;
 
         float cin_cur[32], cin_nxt[32];
@@ -257,19 +269,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int t_row0 = 0, t_colbase = 0;              // tile of the chunk being loaded
         int cur_row0 = 0, cur_col0 = 0;             // chunk being finished
         bool cur_ok = false;
+        const GemmParams* lp = &p0;                 // problem of the chunk being loaded / finished
+        const GemmParams* cp = &p0;
+        float l_alpha = 0.f, l_hs = 0.f, c_alpha = 0.f, c_hs = 0.f;
 #pragma unroll 1
         for (int i = 0; i <= nchunks; ++i) {
             int nx_col0 = 0;
             bool nx_ok = false;
             if (i < nchunks) {
                 if ((i & 3) == 0) {
+                    const int t = first_tile + (i >> 2) * tile_step;
                     int mt, nt;
-                    tile_coords(first_tile + (i >> 2) * tile_step, num_m, num_n, mt, nt);
+                    if (t >= tiles0) { lp = &p1; tile_coords(t - tiles0, num_m1, num_n1, mt, nt); }
+                    else { lp = &p0; tile_coords(t, num_m0, num_n0, mt, nt); }
                     t_row0 = mt * BM * kCG + cta_rank * BM + q * 32;
                     t_colbase = nt * BN + half * 128;
+                    l_alpha = lp->alpha;
+                    if (lp->alpha_p1) l_alpha *= __ldg(lp->alpha_p1);
+                    if (lp->alpha_p2) l_alpha *= __ldg(lp->alpha_p2);
+                    l_hs = lp->hscale;
+                    if (lp->hscale_p) l_hs *= __ldg(lp->hscale_p);
                 }
                 nx_col0 = t_colbase + (i & 3) * 32;
-                nx_ok = (t_row0 < p.M) && (nx_col0 < p.N);
+                nx_ok = (t_row0 < lp->M) && (nx_col0 < lp->N);
             }
             uint32_t v[32];
             if (i > 0) {
@@ -281,7 +303,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ptx::tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + as * BN + half * 128 + c * 32, v);
             }
-            if (i < nchunks && has_cin) epi_load<kRagged>(cin_nxt, p, t_row0 + lane, nx_col0, nx_ok);
+            if (i < nchunks) {
+                if (lp->Cin != nullptr) {
+                    epi_load<kRagged>(cin_nxt, *lp, t_row0 + lane, nx_col0, nx_ok);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cin_nxt[j] = 0.f;
+                }
+            }
             if (i > 0) {
                 ptx::tmem_ld_wait();
                 if (((i - 1) & 3) == 3) {
@@ -294,14 +323,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else ptx::mbar_arrive_cluster(&tempty[as], 0);
                     }
                 }
-                epi_store<kRagged>(v, cin_cur, p, alpha, hs, cur_row0 + lane, cur_col0, cur_ok, mx);
+                epi_store<kRagged>(v, cin_cur, *cp, c_alpha, c_hs, cur_row0 + lane, cur_col0, cur_ok, mx);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) cin_cur[j] = cin_nxt[j];
             cur_row0 = t_row0; cur_col0 = nx_col0; cur_ok = nx_ok;
+            cp = lp; c_alpha = l_alpha; c_hs = l_hs;
         }
-        const float hmax = p.bf16 ? 3.0e38f : 65504.f;
-        if (p.status && __any_sync(0xffffffffu, mx > hmax) && lane == 0) atomicOr(p.status, 1);
+        const float hmax = p0.bf16 ? 3.0e38f : 65504.f;
+        if (p0.status && __any_sync(0xffffffffu, mx > hmax) && lane == 0) atomicOr(p0.status, 1);
     }
 
     // ---------------------------------------------------------------- teardown
@@ -328,13 +358,14 @@ EncodeFn get_encode_fn() {
 }
 
 template <int kCG, bool kAMN, bool kRagged>
-int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
-                   cudaStream_t stream) {
+int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, const CUtensorMap* tmA1,
+                   const CUtensorMap* tmB1, const GemmParams& p1, int max_sms, cudaStream_t stream) {
     using C = Cfg<kCG>;
     auto kern = gemm_tc_kernel<kCG, kAMN, kRagged>;
     const int num_m = (p.M + BM * kCG - 1) / (BM * kCG);
     const int num_n = (p.N + BN - 1) / BN;
     long long want = (long long)num_m * num_n * kCG;
+    if (p1.M > 0) want += (long long)((p1.M + BM * kCG - 1) / (BM * kCG)) * ((p1.N + BN - 1) / BN) * kCG;
     int grid = (int)(want < max_sms ? want : max_sms);
     grid -= grid % kCG;
     if (grid < kCG) grid = kCG;
@@ -344,14 +375,16 @@ int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmPar
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = kCG;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, p);
+    cfg.numAttrs = p.pdl ? 2 : 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, p, *tmA1, *tmB1, p1);
 }
 
 template <int kCG, bool kAMN, bool kRagged>
@@ -399,10 +432,19 @@ void gemm_box_shapes(int variant, uint32_t* a_box_rows, uint32_t* a_box_cols, ui
     *b_box_cols = cg2 ? BN / 2 : BN;
 }
 
-int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
-                   cudaStream_t stream) {
+int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p,
+                    const CUtensorMap* tmA1, const CUtensorMap* tmB1, const GemmParams* p1_or_null, int max_sms,
+                    cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0) return 0;
     if (p.K <= 0 || p.K % BK != 0) return (int)cudaErrorInvalidValue;
+    GemmParams p1{};
+    if (p1_or_null && p1_or_null->M > 0 && p1_or_null->N > 0) {
+        p1 = *p1_or_null;
+        if (p1.K <= 0 || p1.K % BK != 0 || p1.bf16 != p.bf16) return (int)cudaErrorInvalidValue;
+    } else {
+        tmA1 = tmA;
+        tmB1 = tmB;
+    }
     if (max_sms <= 0) {
         static int sms = 0;
         if (!sms) {
@@ -413,23 +455,31 @@ int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, 
         max_sms = sms;
     }
     // aligned fast path: whole 32 x 32 epilogue chunks (the factorization only ever issues these)
-    const bool ragged = (p.M % 32) || (p.N % 32) || (p.H && (p.h_cols % 32) && p.h_cols < p.N);
+    auto is_ragged = [](const GemmParams& g) {
+        return (g.M % 32) || (g.N % 32) || (g.H && (g.h_cols % 32) && g.h_cols < g.N);
+    };
+    const bool ragged = is_ragged(p) || (p1.M > 0 && is_ragged(p1));
     if (!ragged) {
         switch (variant) {
-            case GEMM_CG1_AMN: return launch_variant<1, true, false>(tmA, tmB, p, max_sms, stream);
-            case GEMM_CG2_AMN: return launch_variant<2, true, false>(tmA, tmB, p, max_sms, stream);
-            case GEMM_CG1_AK: return launch_variant<1, false, false>(tmA, tmB, p, max_sms, stream);
-            case GEMM_CG2_AK: return launch_variant<2, false, false>(tmA, tmB, p, max_sms, stream);
+            case GEMM_CG1_AMN: return launch_variant<1, true, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+            case GEMM_CG2_AMN: return launch_variant<2, true, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+            case GEMM_CG1_AK: return launch_variant<1, false, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+            case GEMM_CG2_AK: return launch_variant<2, false, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
             default: return (int)cudaErrorInvalidValue;
         }
     }
     switch (variant) {
-        case GEMM_CG1_AMN: return launch_variant<1, true, true>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG2_AMN: return launch_variant<2, true, true>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG1_AK: return launch_variant<1, false, true>(tmA, tmB, p, max_sms, stream);
-        case GEMM_CG2_AK: return launch_variant<2, false, true>(tmA, tmB, p, max_sms, stream);
+        case GEMM_CG1_AMN: return launch_variant<1, true, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+        case GEMM_CG2_AMN: return launch_variant<2, true, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+        case GEMM_CG1_AK: return launch_variant<1, false, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+        case GEMM_CG2_AK: return launch_variant<2, false, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
         default: return (int)cudaErrorInvalidValue;
     }
+}
+
+int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
+                   cudaStream_t stream) {
+    return launch_gemm_tc2(variant, tmA, tmB, p, nullptr, nullptr, nullptr, max_sms, stream);
 }
 
 }  // namespace mplu

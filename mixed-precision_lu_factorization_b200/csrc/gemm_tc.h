@@ -38,6 +38,7 @@ struct GemmParams {
     const float* hscale_p;
     int bf16;     // 0 = fp16 operands/shadow, 1 = bf16
     int* status;  // device word; bit 0 set when a shadow value overflowed the 16-bit range
+    int pdl;      // 1 = launch with programmatic stream serialization (prologue overlaps the predecessor's tail)
 };
 
 // Build a 2-D TMA map (SWIZZLE_128B, 16-bit elements) over a column-major parent array with `rows` x `cols`
@@ -55,5 +56,11 @@ int gemm_tc_init();
 // Launch on `stream` using at most `max_sms` SMs (0 = all).  Returns cudaError_t as int.
 int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
                    cudaStream_t stream);
+
+// Grouped launch: a second, independent problem (same variant and element type) rides in the same kernel; its tiles
+// follow the first problem's.  p1 == nullptr (or empty) degenerates to launch_gemm_tc.
+int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p,
+                    const CUtensorMap* tmA1, const CUtensorMap* tmB1, const GemmParams* p1, int max_sms,
+                    cudaStream_t stream);
 
 }  // namespace mplu

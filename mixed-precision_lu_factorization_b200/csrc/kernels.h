@@ -25,10 +25,14 @@ int launch_first_touch(const double* A, long long lda, int n, float* W, long lon
 int launch_scales(const float* amax, float* scales, int target_exp_a, int exp_l, int bf16, cudaStream_t st);
 int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, int rows, int cols, const float* scale,
                        int bf16, int* status, cudaStream_t st);
-// inv_scales[4*blk + {0,1,2,3}] = {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv}
-int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, float* Linv32, float* Uinv32,
-                   float* inv_scales, int blk, int bf16, int* status, cudaStream_t st,
-                   long long* dbg_clk = nullptr);  // dbg_clk: optional device array of phase time stamps (clock64)
+// No-pivot LU of the 128x128 block at W(k0,k0) + its explicit inverses.  Linv16/Uinv16 point at the block's origin
+// inside the 16-bit inverse bands (leading dimension ld16); Linv32/Uinv32 are the fp32 copies for the triangular
+// solves, indexed by blk.  tile_scales[0..3] = {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv} of the enclosing diagonal tile:
+// written when first_in_tile, read otherwise.
+int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, long long ld16, float* Linv32,
+                   float* Uinv32, float* tile_scales, int first_in_tile, int blk, int bf16, int* status, cudaStream_t st,
+                   long long* dbg_clk = nullptr,  // optional device array of phase time stamps (clock64)
+                   int pdl = 0);                  // 1 = programmatic dependent launch
 
 // ir.cu
 // r = b - A*x (fp64), ||r||_inf and ||x||_inf into norms[0], norms[1]

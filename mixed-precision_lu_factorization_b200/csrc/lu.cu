@@ -1,13 +1,17 @@
 // Host orchestration of the blocked right-looking no-pivot LU + fp64 iterative refinement, and the C ABI of
 // include/mplu.h.  This is the B200-native counterpart of the panel loop in /root/reference/MPF.cu:100-241:
 //   reference per panel (r = 32):  gather -> fp16 pivot search -> LASWP -> fp64 panel LU -> Dtrsm -> rank-32 Dgemm
-//   here per outer block (nb = 2048): the tall panel is factored RECURSIVELY (halving down to 128-wide leaves:
-//   diag_lu + L21 = A21*inv(U11) on the tensor cores), the block row by a recursive TRSM whose leaves multiply with
-//   the explicit 128x128 inverses, then one rank-nb tcgen05 trailing update; operands are 16-bit shadows,
-//   accumulation and the working matrix are fp32.
-// Look-ahead: the trailing update of step k is split into the next panel's columns (done first) and the rest; the
-// next panel is factored on a second stream restricted to `side_sms` SMs while the rest of the update runs on the
-// others.  The whole schedule is captured once into a CUDA graph per (n, options) and replayed.
+//   here per diagonal tile (nb = 1024..2048), all products on the tcgen05 GEMM with 16-bit operands, fp32 accumulate:
+//     GETRF   the nb x nb diagonal tile, recursively, CARRYING EXPLICIT INVERSES: a 128x128 leaf (diag_lu) returns
+//             L11\U11, inv(L11), inv(U11); a node of width w = 2h does  U12 = inv(La) A12,  L21 = A21 inv(Ua),
+//             A22 -= L21 U12, recurses, then merges  inv(L) = [inv(La) 0; -inv(Lb) L21 inv(La), inv(Lb)]  (same for U)
+//     TRSM    L panel = A21 inv(U11) and U panel = inv(L11) A12: ONE GEMM each with the tile's nb x nb inverse
+//             (replaces cublasDtrsm, MPF.cu:215-225, and the 2*nb/128-1 dependent launches of a recursive TRSM)
+//     GEMM    A22 -= L21 U12 (replaces cublasDgemm, MPF.cu:230-239)
+// Two lanes (streams with disjoint SM budgets), depth-1 look-ahead:
+//   chain lane: TRSM of the NEXT tile's rows/columns -> update of the next diagonal tile -> GETRF of it   (critical path)
+//   bulk lane:  TRSM of the remaining rows/columns -> update of the next block column/row -> rest of the trailing matrix
+// The whole schedule is captured once into a CUDA graph per (n, options) and replayed.
 // No host<->device round trips inside the loop (the reference does one per panel, MPF.cu:146,158).
 #include "../../include/mplu.h"
 #include "gemm_tc.h"
@@ -30,9 +34,13 @@ struct mplu_context {
     mplu_options opts{};
     // working storage
     float* W = nullptr;       // npad x npad fp32, column-major (ld = npad): becomes L\U
-    uint16_t* Wh = nullptr;   // npad x npad 16-bit shadow (scaled), same indexing
-    uint16_t* Linv16 = nullptr;  // 128 x npad : block j at columns [128j, 128j+128)
+    uint16_t* Wh = nullptr;   // npad x npad 16-bit shadow of the not yet factored (trailing) part, A-type scale
+    uint16_t* Fh = nullptr;   // npad x npad 16-bit shadow of the FACTORS: L part scaled SC_L, U part scaled SC_A
+    uint16_t* Linv16 = nullptr;  // nbcap x npad band: inverse of the L factor of tile [T, T+nb) at rows [0,nb), cols [T,T+nb)
     uint16_t* Uinv16 = nullptr;
+    uint16_t* Tb1 = nullptr;     // nbcap x nbcap scratch of the inverse merges (L side, U side)
+    uint16_t* Tb2 = nullptr;
+    int cap_nb = 0;
     float* Linv32 = nullptr;
     float* Uinv32 = nullptr;
     float* inv_scales = nullptr;  // 4 per diagonal block
@@ -51,14 +59,20 @@ struct mplu_context {
     // staging for the host variant
     double* dA_stage = nullptr; size_t dA_cap = 0;
     double* db_stage = nullptr; double* dx_stage = nullptr; size_t dv_cap = 0;
-    // tensor maps
-    CUtensorMap tmWh_A, tmWh_B1, tmWh_B2, tmLinv_A, tmUinv_B1, tmUinv_B2;
+    // GEMM operand views (tensor maps) of the 16-bit arrays
+    struct Operand16 {
+        uint16_t* base = nullptr;
+        long long ld = 0;
+        CUtensorMap mapA, mapB1, mapB2;  // as A operand (64x64 boxes), as B operand for 1-CTA / CTA-pair tiles
+    } opWh, opFh, opLinv, opUinv, opT1, opT2;
     int gemm_launches = 0, kernel_launches = 0;
     // look-ahead / graph
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static constexpr int kMaxSteps = 512;
+    cudaEvent_t ev_step[4 * kMaxSteps] = {};  // per step: GETRF done, next-tile TRSM done, b2 done, b3a done
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp; const void* W; } gkey{};
+    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group; const void* W; } gkey{};
     int g_gemm_launches = 0, g_kernel_launches = 0, g_trail_count = 0;
     double g_trail_flops = 0, g_trail_bytes = 0;
     bool capturing = false;
@@ -68,6 +82,12 @@ struct mplu_context {
     cudaEvent_t trail_ev[2 * kMaxTrail] = {};
     int trail_count = 0;
     double trail_flops = 0, trail_bytes = 0;
+    // optional timeline marks (development aid, mplu_debug_timeline): tag + event
+    static constexpr int kMaxMarks = 4096;
+    cudaEvent_t mark_ev[kMaxMarks] = {};
+    int mark_tag[kMaxMarks] = {};
+    int mark_count = 0;
+    bool marks_on = false;
 };
 
 namespace {
@@ -85,41 +105,67 @@ namespace {
 
 void free_work(mplu_context* c) {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    cudaFree(c->W); cudaFree(c->Wh); cudaFree(c->Linv16); cudaFree(c->Uinv16); cudaFree(c->Linv32); cudaFree(c->Uinv32);
+    cudaFree(c->W); cudaFree(c->Wh); cudaFree(c->Fh); cudaFree(c->Linv16); cudaFree(c->Uinv16); cudaFree(c->Linv32);
+    cudaFree(c->Uinv32); cudaFree(c->Tb1); cudaFree(c->Tb2);
     cudaFree(c->inv_scales); cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
-    c->W = nullptr; c->Wh = nullptr; c->Linv16 = c->Uinv16 = nullptr; c->Linv32 = c->Uinv32 = nullptr;
+    c->W = nullptr; c->Wh = c->Fh = nullptr; c->Linv16 = c->Uinv16 = c->Tb1 = c->Tb2 = nullptr;
+    c->Linv32 = c->Uinv32 = nullptr; c->cap_nb = 0;
     c->inv_scales = nullptr; c->rowsum_part = nullptr; c->r = c->partial = nullptr; c->y = nullptr;
     c->cap_npad = 0;
+}
+
+int effective_nb(const mplu_context* c, int npad) {
+    int NB = c->opts.nb;
+    if (NB < kDiagBlock) NB = kDiagBlock;
+    NB = (NB / kDiagBlock) * kDiagBlock;
+    return NB > npad ? npad : NB;
+}
+
+int make_operand(mplu_context::Operand16* o, uint16_t* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    o->base = base;
+    o->ld = (long long)ld;
+    if (make_tmap_16bit(&o->mapA, base, rows, cols, ld, 64, 64)) return MPLU_E_TMAP;
+    if (make_tmap_16bit(&o->mapB1, base, rows, cols, ld, 64, 256)) return MPLU_E_TMAP;
+    if (make_tmap_16bit(&o->mapB2, base, rows, cols, ld, 64, 128)) return MPLU_E_TMAP;
+    return 0;
 }
 
 int ensure_work(mplu_context* c, int n) {
     const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
     c->n = n;
     c->npad = npad;
-    if (npad > c->cap_npad) {
+    const int NB = effective_nb(c, npad);
+    if (npad > c->cap_npad || NB > c->cap_nb) {
         free_work(c);
-        const size_t np = (size_t)npad;
+        const size_t np = (size_t)npad, nb = (size_t)NB;
         CK(cudaMalloc(&c->W, np * np * sizeof(float)));
         CK(cudaMalloc(&c->Wh, np * np * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Linv16, np * kDiagBlock * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Uinv16, np * kDiagBlock * sizeof(uint16_t)));
+        CK(cudaMalloc(&c->Fh, np * np * sizeof(uint16_t)));
+        CK(cudaMalloc(&c->Linv16, np * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&c->Uinv16, np * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&c->Tb1, nb * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&c->Tb2, nb * nb * sizeof(uint16_t)));
         CK(cudaMalloc(&c->Linv32, np * kDiagBlock * sizeof(float)));
         CK(cudaMalloc(&c->Uinv32, np * kDiagBlock * sizeof(float)));
+        // diag_lu only stores the triangles of the fp32 inverses: the other halves stay zero from here on
+        CK(cudaMemset(c->Linv32, 0, np * kDiagBlock * sizeof(float)));
+        CK(cudaMemset(c->Uinv32, 0, np * kDiagBlock * sizeof(float)));
         CK(cudaMalloc(&c->inv_scales, 4 * (np / kDiagBlock) * sizeof(float)));
         CK(cudaMalloc(&c->rowsum_part, (size_t)c->nchunk * np * sizeof(double)));
         CK(cudaMalloc(&c->r, np * sizeof(double)));
         CK(cudaMalloc(&c->partial, (size_t)c->nchunk * np * sizeof(double)));
         CK(cudaMalloc(&c->y, 2 * np * sizeof(float)));
         c->cap_npad = npad;
+        c->cap_nb = NB;
     }
-    // tensor maps over the parents (dims = npad so that out-of-range boxes are zero filled)
-    const uint64_t np = (uint64_t)npad;
-    if (make_tmap_16bit(&c->tmWh_A, c->Wh, np, np, np, 64, 64)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&c->tmWh_B1, c->Wh, np, np, np, 64, 256)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&c->tmWh_B2, c->Wh, np, np, np, 64, 128)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&c->tmLinv_A, c->Linv16, kDiagBlock, np, kDiagBlock, 64, 64)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&c->tmUinv_B1, c->Uinv16, kDiagBlock, np, kDiagBlock, 64, 256)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&c->tmUinv_B2, c->Uinv16, kDiagBlock, np, kDiagBlock, 64, 128)) return MPLU_E_TMAP;
+    // operand views over the parents (dims = allocation so that out-of-range boxes are zero filled)
+    const uint64_t np = (uint64_t)npad, nbc = (uint64_t)c->cap_nb;
+    CKI(make_operand(&c->opWh, c->Wh, np, np, np));
+    CKI(make_operand(&c->opFh, c->Fh, np, np, np));
+    CKI(make_operand(&c->opLinv, c->Linv16, nbc, np, nbc));
+    CKI(make_operand(&c->opUinv, c->Uinv16, nbc, np, nbc));
+    CKI(make_operand(&c->opT1, c->Tb1, nbc, nbc, nbc));
+    CKI(make_operand(&c->opT2, c->Tb2, nbc, nbc, nbc));
     return 0;
 }
 
@@ -127,17 +173,20 @@ void resolve_options(mplu_context* c, int n) {
     if (c->opts.nb <= 0) c->opts.nb = n >= 12288 ? 2048 : (n >= 4096 ? 1024 : 512);
 }
 
+using Operand16 = mplu_context::Operand16;
+
 struct GemmCall {
-    // A operand: 0 = Wh block, 1 = Linv16 block ; B operand: 0 = Wh block, 1 = Uinv16 block
-    int a_kind, a_r0, a_c0;
-    int b_kind, b_r0, b_c0;
+    const Operand16* A; int a_r0, a_c0;  // A block origin inside its parent (row m0, col k0)
+    const Operand16* B; int b_r0, b_c0;  // B block origin inside its parent (row k0, col n0)
     int M, N, K;
-    int out_r0, out_c0;  // block origin in W / Wh
-    bool accumulate;     // out = W + alpha*acc (else alpha*acc)
+    float* C; long long ldc;             // fp32 output (null: none), already offset to the block origin
+    bool accumulate;                     // out = C + alpha*acc (else alpha*acc)
+    uint16_t* H; long long ldh;          // 16-bit output (null: none), already offset
+    int h_rows, h_cols;                  // H is written where (m < h_rows || n < h_cols)
+    float alpha;                         // static factor times *alpha_p1 times *alpha_p2 (device, null = 1)
     const float* alpha_p1;
     const float* alpha_p2;
-    const float* hscale_p;
-    int h_rows, h_cols;
+    const float* hscale_p;               // H = cvt16(out * *hscale_p)
 };
 
 // Where a piece of the schedule runs: stream + SM budget (0 = all SMs).
@@ -146,105 +195,173 @@ struct Lane {
     int sms;
 };
 
-int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
-    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
-    int variant;
-    if (c->opts.gemm_variant == MPLU_GEMM_CG1) variant = GEMM_CG1_AMN;
-    else variant = (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
-    const bool cg2 = (variant == GEMM_CG2_AMN);
-    const CUtensorMap* tmA = g.a_kind == 0 ? &c->tmWh_A : &c->tmLinv_A;
-    const CUtensorMap* tmB = g.b_kind == 0 ? (cg2 ? &c->tmWh_B2 : &c->tmWh_B1) : (cg2 ? &c->tmUinv_B2 : &c->tmUinv_B1);
+GemmParams gemm_params(const mplu_context* c, const GemmCall& g) {
     GemmParams p{};
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.a_r0 = g.a_r0; p.a_c0 = g.a_c0; p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
-    const long long ld = c->npad;
-    p.C = c->W + g.out_r0 + (long long)g.out_c0 * ld;
-    p.ldc = ld;
-    p.Cin = g.accumulate ? p.C : nullptr;
-    p.ldcin = ld;
-    p.H = c->Wh + g.out_r0 + (long long)g.out_c0 * ld;
-    p.ldh = ld;
+    p.C = g.C; p.ldc = g.ldc;
+    p.Cin = g.accumulate ? g.C : nullptr; p.ldcin = g.ldc;
+    p.H = g.H; p.ldh = g.ldh;
     p.h_rows = g.h_rows; p.h_cols = g.h_cols;
-    p.alpha = 1.f; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2;
+    p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2;
     p.hscale = 1.f; p.hscale_p = g.hscale_p;
     p.bf16 = c->opts.precision == MPLU_BF16;
     p.status = c->status;
-    c->gemm_launches++;
-    c->kernel_launches++;
+    p.pdl = c->opts.pdl;
+    return p;
+}
+
+int pick_variant(const mplu_context* c, const GemmCall& g) {
+    if (c->opts.gemm_variant == MPLU_GEMM_CG1) return GEMM_CG1_AMN;
+    return (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
+}
+
+int lane_sms(const mplu_context* c, const Lane& ln) {
     int sms = ln.sms > 0 ? ln.sms : c->num_sms;
     if (c->opts.max_sms > 0 && c->opts.max_sms < sms) sms = c->opts.max_sms;
-    return launch_gemm_tc(variant, tmA, tmB, p, sms, ln.st);
+    return sms;
+}
+
+int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    const int variant = pick_variant(c, g);
+    const bool cg2 = (variant == GEMM_CG2_AMN);
+    const GemmParams p = gemm_params(c, g);
+    c->gemm_launches++;
+    c->kernel_launches++;
+    return launch_gemm_tc(variant, &g.A->mapA, cg2 ? &g.B->mapB2 : &g.B->mapB1, p, lane_sms(c, ln), ln.st);
+}
+
+// Two independent products in ONE launch (grouped GEMM) when they use the same tile variant, else two launches.
+int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const GemmCall& g1) {
+    const bool e0 = g0.M <= 0 || g0.N <= 0 || g0.K <= 0, e1 = g1.M <= 0 || g1.N <= 0 || g1.K <= 0;
+    if (e0) return e1 ? 0 : run_gemm(c, ln, g1);
+    if (e1) return run_gemm(c, ln, g0);
+    const int variant = pick_variant(c, g0);
+    if (!c->opts.group || variant != pick_variant(c, g1)) {
+        CKI(run_gemm(c, ln, g0));
+        return run_gemm(c, ln, g1);
+    }
+    const bool cg2 = (variant == GEMM_CG2_AMN);
+    const GemmParams p0 = gemm_params(c, g0), p1 = gemm_params(c, g1);
+    c->gemm_launches++;
+    c->kernel_launches++;
+    return launch_gemm_tc2(variant, &g0.A->mapA, cg2 ? &g0.B->mapB2 : &g0.B->mapB1, p0, &g1.A->mapA,
+                           cg2 ? &g1.B->mapB2 : &g1.B->mapB1, &p1, lane_sms(c, ln), ln.st);
 }
 
 inline int split_width(int w) { return kDiagBlock * ((w / kDiagBlock + 1) / 2); }
 
-// A[r0:r1, c0:c1) -= L[r0:r1, k0:k1) * U[k0:k1, c0:c1)   (Schur update; the result is A-type, shadow where asked)
-int schur_update(mplu_context* c, const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows,
-                 int h_cols) {
-    GemmCall g{0, r0, k0, 0, k0, c0, r1 - r0, c1 - c0, k1 - k0, r0, c0, true,
-               c->scales + SC_NEG_LA_INV, nullptr, c->scales + SC_A, h_rows, h_cols};
-    return run_gemm(c, ln, g);
-}
+struct Sched {
+    mplu_context* c;
+    long long ld;   // npad
+    long long ldi;  // leading dimension of the inverse bands and merge scratch (cap_nb)
+    float* Wp(int r, int col) const { return c->W + r + (long long)col * ld; }
+    uint16_t* Whp(int r, int col) const { return c->Wh + r + (long long)col * ld; }
+    uint16_t* Fhp(int r, int col) const { return c->Fh + r + (long long)col * ld; }
+    const float* sc(int i) const { return c->scales + i; }
+    // scales of the diagonal tile starting at column T: {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv}
+    float* ts(int T) const { return c->inv_scales + 4 * (T / kDiagBlock); }
 
-// U[c0:c0+w, n0:n1) = inv(L11[c0:c0+w)) * A[c0:c0+w, n0:n1), in place; recursive, 128-wide leaves multiply with the
-// explicit inverse of the diagonal block (replaces cublasDtrsm, MPF.cu:215-225).
-int trsm_rec(mplu_context* c, const Lane& ln, int c0, int w, int n0, int n1) {
-    if (n1 <= n0) return 0;
-    if (w <= kDiagBlock) {
-        const int blk = c0 / kDiagBlock;
-        GemmCall t{1, 0, blk * kDiagBlock, 0, c0, n0, kDiagBlock, n1 - n0, kDiagBlock, c0, n0, false,
-                   c->inv_scales + 4 * blk + 1, c->scales + SC_A_INV, c->scales + SC_A, kDiagBlock, n1 - n0};
-        return run_gemm(c, ln, t);
+    // A[r0:r1, c0:c1) -= L[r0:r1, k0:k1) * U[k0:k1, c0:c1): operands from the factor shadow Fh, result in W and,
+    // where asked, in the trailing shadow Wh (the reference's cublasDgemm, MPF.cu:230-239)
+    GemmCall schur_call(int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
+        return GemmCall{&c->opFh, r0, k0, &c->opFh, k0, c0, r1 - r0, c1 - c0, k1 - k0, Wp(r0, c0), ld, true,
+                        Whp(r0, c0), ld, h_rows, h_cols, 1.f, sc(SC_NEG_LA_INV), nullptr, sc(SC_A)};
     }
-    const int h = split_width(w);
-    CKI(trsm_rec(c, ln, c0, h, n0, n1));
-    CKI(schur_update(c, ln, c0 + h, c0 + w, n0, n1, c0, c0 + h, w - h, n1 - n0));
-    return trsm_rec(c, ln, c0 + h, w - h, n0, n1);
-}
-
-// LU of the tall panel: columns [c0, c0+w), rows [c0, npad); recursive halving down to one diagonal block.
-int panel_rec(mplu_context* c, const Lane& ln, int c0, int w) {
-    const int npad = c->npad;
-    if (w <= kDiagBlock) {
-        const int blk = c0 / kDiagBlock;
-        CKI(launch_diag_lu(c->W, npad, c0, c->Linv16, c->Uinv16, c->Linv32, c->Uinv32, c->inv_scales, blk,
-                           c->opts.precision == MPLU_BF16, c->status, ln.st));
-        c->kernel_launches++;
-        const int below = c0 + kDiagBlock;
-        if (npad > below) {  // L21 = A21 * inv(U11), in place
-            GemmCall g{0, below, c0, 1, 0, blk * kDiagBlock, npad - below, kDiagBlock, kDiagBlock, below, c0, false,
-                       c->scales + SC_A_INV, c->inv_scales + 4 * blk + 3, c->scales + SC_L, npad - below, kDiagBlock};
-            CKI(run_gemm(c, ln, g));
+    int schur(const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
+        return run_gemm(c, ln, schur_call(r0, r1, c0, c1, k0, k1, h_rows, h_cols));
+    }
+    // U[k0:k0+w, c0:c1) = inv(L[k0:k0+w)) * A[k0:k0+w, c0:c1)   (inverse of the block inside tile T, one GEMM)
+    GemmCall trsm_u_call(int T, int k0, int w, int c0, int c1) const {
+        return GemmCall{&c->opLinv, k0 - T, k0, &c->opWh, k0, c0, w, c1 - c0, w, Wp(k0, c0), ld, false,
+                        Fhp(k0, c0), ld, w, c1 - c0, 1.f, ts(T) + 1, sc(SC_A_INV), sc(SC_A)};
+    }
+    int trsm_u(const Lane& ln, int T, int k0, int w, int c0, int c1) const {
+        return run_gemm(c, ln, trsm_u_call(T, k0, w, c0, c1));
+    }
+    // L[r0:r1, k0:k0+w) = A[r0:r1, k0:k0+w) * inv(U[k0:k0+w))
+    GemmCall trsm_l_call(int T, int k0, int w, int r0, int r1) const {
+        return GemmCall{&c->opWh, r0, k0, &c->opUinv, k0 - T, k0, r1 - r0, w, w, Wp(r0, k0), ld, false,
+                        Fhp(r0, k0), ld, r1 - r0, w, 1.f, sc(SC_A_INV), ts(T) + 3, sc(SC_L)};
+    }
+    int trsm_l(const Lane& ln, int T, int k0, int w, int r0, int r1) const {
+        return run_gemm(c, ln, trsm_l_call(T, k0, w, r0, r1));
+    }
+    // both panel solves of one step in a single grouped launch
+    int trsm_lu(const Lane& ln, int T, int k0, int w, int lo, int hi) const {
+        return run_gemm_pair(c, ln, trsm_l_call(T, k0, w, lo, hi), trsm_u_call(T, k0, w, lo, hi));
+    }
+    // GETRF of the diagonal block [c0, c0+w)^2 inside tile T, leaving inv(L), inv(U) of the block in the bands.
+    int getrf(const Lane& ln, int T, int c0, int w) const {
+        if (w <= kDiagBlock) {
+            const int blk = c0 / kDiagBlock;
+            uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
+            uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
+            CKI(launch_diag_lu(c->W, ld, c0, l16, u16, ldi, c->Linv32, c->Uinv32, ts(T), c0 == T, blk,
+                               c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, c->opts.pdl));
+            c->kernel_launches++;
+            return 0;
         }
-        return 0;
+        const int h = split_width(w), g = w - h, c1 = c0 + h;
+        CKI(getrf(ln, T, c0, h));
+        CKI(trsm_lu(ln, T, c0, h, c1, c0 + w));
+        CKI(schur(ln, c1, c0 + w, c1, c0 + w, c0, c1, g, g));
+        CKI(getrf(ln, T, c1, g));
+        // merge the inverses:  inv(L)21 = -inv(Lb) * (L21 * inv(La)),  inv(U)12 = -(inv(Ua) * U12) * inv(Ub);
+        // the L-side and U-side products are independent and share launches
+        GemmCall tl{&c->opFh, c1, c0, &c->opLinv, c0 - T, c0, g, h, h, nullptr, 0, false,
+                    c->Tb1, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L)};
+        GemmCall tu{&c->opUinv, c0 - T, c0, &c->opFh, c0, c1, h, g, h, nullptr, 0, false,
+                    c->Tb2, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L)};
+        CKI(run_gemm_pair(c, ln, tl, tu));
+        GemmCall x{&c->opLinv, c1 - T, c1, &c->opT1, 0, 0, g, h, g, nullptr, 0, false,
+                   c->Linv16 + (c1 - T) + (long long)c0 * ldi, ldi, g, h, -1.f, ts(T) + 1, sc(SC_L_INV), ts(T) + 0};
+        GemmCall y{&c->opT2, 0, 0, &c->opUinv, c1 - T, c1, h, g, g, nullptr, 0, false,
+                   c->Uinv16 + (c0 - T) + (long long)c1 * ldi, ldi, h, g, -1.f, sc(SC_L_INV), ts(T) + 3, ts(T) + 2};
+        return run_gemm_pair(c, ln, x, y);
     }
-    const int h = split_width(w);
-    CKI(panel_rec(c, ln, c0, h));
-    CKI(trsm_rec(c, ln, c0, h, c0 + h, c0 + w));
-    CKI(schur_update(c, ln, c0 + h, npad, c0 + h, c0 + w, c0, c0 + h, npad - c0 - h, w - h));
-    return panel_rec(c, ln, c0 + h, w - h);
-}
+};
 
 int record_event(mplu_context* c, cudaEvent_t ev, cudaStream_t st) {
     return (int)cudaEventRecordWithFlags(ev, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
-// Everything after the first touch: scales, shadows of the first block column / block row, the panel loop.
+// timeline mark: tag = 1000*kind + step; kinds: 1 chain: next-tile TRSM start, 2 chain: GETRF start, 3 chain: GETRF end,
+// 4 bulk: TRSM start, 5 bulk: block column/row update start, 6 bulk: rest start, 7 bulk: rest end
+int mark(mplu_context* c, int tag, cudaStream_t st) {
+    if (!c->marks_on || c->mark_count >= mplu_context::kMaxMarks) return 0;
+    cudaEvent_t& e = c->mark_ev[c->mark_count];
+    if (!e) CK(cudaEventCreate(&e));
+    c->mark_tag[c->mark_count++] = tag;
+    return record_event(c, e, st);
+}
+
+int step_event(mplu_context* c, int step, int kind, cudaEvent_t* out) {
+    if (step >= mplu_context::kMaxSteps) return MPLU_E_ARG;
+    cudaEvent_t& e = c->ev_step[4 * step + kind];
+    if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = e;
+    return 0;
+}
+
+// Everything after the first touch: scales, shadows of the first block column / block row, the tile loop.
 int enqueue_factorization(mplu_context* c) {
     const int npad = c->npad;
     const long long ld = npad;
     const int bf16 = c->opts.precision == MPLU_BF16;
-    int NB = c->opts.nb;
-    if (NB < kDiagBlock) NB = kDiagBlock;
-    NB = (NB / kDiagBlock) * kDiagBlock;
-    if (NB > npad) NB = npad;
+    const int NB = effective_nb(c, npad);
+    if ((npad + NB - 1) / NB >= mplu_context::kMaxSteps) return MPLU_E_ARG;
     cudaStream_t st = c->stream;
-    int side_sms = c->opts.side_sms > 0 ? c->opts.side_sms : 24;
+    int side_sms = c->opts.side_sms > 0 ? c->opts.side_sms : 32;
     side_sms -= side_sms % 2;
-    const bool lookahead = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16;
+    const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && npad > 2 * NB;
     const Lane all{st, 0};
-    const Lane main_part{st, c->num_sms - side_sms};
-    const Lane side{c->side, side_sms};
+    const Lane bulk = two ? Lane{st, c->num_sms - side_sms} : all;
+    const Lane chain = two ? Lane{c->side, side_sms} : all;
+    const Sched S{c, ld, (long long)c->cap_nb};
+    enum { EV_GETRF = 0, EV_NEXT = 1, EV_B2 = 2, EV_B3A = 3 };
+    cudaEvent_t ev = nullptr;
 
     CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
     CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
@@ -252,46 +369,77 @@ int enqueue_factorization(mplu_context* c) {
         CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
                                c->scales + SC_A, bf16, c->status, st));
     c->kernel_launches += 3;
+    // the inverse bands are only ever written inside the diagonal tiles' triangles: everything else must read 0
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
 
-    CKI(panel_rec(c, all, 0, NB));
-    for (int k = 0; k < npad; k += NB) {
-        const int nbk = (NB < npad - k) ? NB : (npad - k);
-        const int kend = k + nbk;
-        if (kend >= npad) break;
-        const int nbn = (NB < npad - kend) ? NB : (npad - kend);
-        const int cnext = kend + nbn;  // end of the next panel's columns
-        // next panel's columns first: block row of U, then their Schur update (full shadow: the panel consumes it)
-        CKI(trsm_rec(c, all, k, nbk, kend, cnext));
-        CKI(schur_update(c, all, kend, npad, kend, cnext, k, kend, npad - kend, nbn));
-        const bool rest = cnext < npad;
-        const bool fork = lookahead && rest;
-        if (fork) {
-            CK(cudaEventRecord(c->ev_fork, st));
-            CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-            CKI(panel_rec(c, side, kend, nbn));
-            CK(cudaEventRecord(c->ev_join, c->side));
+    CKI(S.getrf(all, 0, 0, NB));
+    if (two) {
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    }
+    int step = 0;
+    for (int k0 = 0; k0 + NB < npad; k0 += NB, ++step) {
+        const int k1 = k0 + NB;
+        const int k2 = (k1 + NB < npad) ? k1 + NB : npad;
+        const int nbn = k2 - k1;
+        // ---- chain lane: panel solves restricted to the next tile, its Schur update, its GETRF
+        if (two && step > 0) {  // tile rows/columns k1.. of block column/row k were updated by the bulk lane
+            CKI(step_event(c, step - 1, EV_B2, &ev));
+            CK(cudaStreamWaitEvent(chain.st, ev, 0));
         }
-        if (rest) {
-            const Lane& ln = fork ? main_part : all;
-            CKI(trsm_rec(c, ln, k, nbk, cnext, npad));
-            const int Mt = npad - kend, Nt = npad - cnext;
-            const bool timed = c->trail_count < mplu_context::kMaxTrail;
-            if (timed) {
-                cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
-                if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
-                CKI(record_event(c, e0, st));
-            }
-            // the rest of the trailing matrix: shadow only for the next panel's block row (its TRSM input)
-            CKI(schur_update(c, ln, kend, npad, cnext, npad, k, kend, nbn, 0));
-            if (timed) {
-                CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], st));
-                c->trail_count++;
-                c->trail_flops += 2.0 * Mt * (double)Nt * nbk;
-                c->trail_bytes += 8.0 * Mt * (double)Nt;
-            }
+        CKI(mark(c, 1000 + step, chain.st));
+        CKI(S.trsm_lu(chain, k0, k0, NB, k1, k2));
+        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (two && step > 0) {  // the next diagonal tile has received update step-1 (first piece of the bulk's rest)
+            CKI(step_event(c, step - 1, EV_B3A, &ev));
+            CK(cudaStreamWaitEvent(chain.st, ev, 0));
         }
-        if (fork) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
-        else CKI(panel_rec(c, all, kend, nbn));
+        CKI(S.schur(chain, k1, k2, k1, k2, k0, k1, nbn, nbn));
+        CKI(mark(c, 2000 + step, chain.st));
+        CKI(S.getrf(chain, k1, k1, nbn));
+        CKI(mark(c, 3000 + step, chain.st));
+        if (two) { CKI(step_event(c, step + 1, EV_GETRF, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        // ---- bulk lane: the other rows/columns of the panels, then the trailing update
+        if (k2 >= npad) continue;
+        if (two && step > 0) {  // GETRF of tile k (its inverses) came from the chain lane
+            CKI(step_event(c, step, EV_GETRF, &ev));
+            CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+        }
+        CKI(mark(c, 4000 + step, bulk.st));
+        CKI(S.trsm_lu(bulk, k0, k0, NB, k2, npad));
+        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CK(cudaStreamWaitEvent(bulk.st, ev, 0)); }
+        CKI(mark(c, 5000 + step, bulk.st));
+        // next block column and next block row (full shadows), one grouped launch
+        CKI(run_gemm_pair(c, bulk, S.schur_call(k2, npad, k1, k2, k0, k1, npad - k2, nbn),
+                          S.schur_call(k1, k2, k2, npad, k0, k1, nbn, npad - k2)));
+        if (two) { CKI(step_event(c, step, EV_B2, &ev)); CK(cudaEventRecord(ev, bulk.st)); }
+        // the rest of the trailing matrix (no shadow), block column k2.. first: the chain lane's next Schur update
+        // only needs the diagonal tile inside it
+        const int k3 = (k2 + NB < npad) ? k2 + NB : npad;
+        CKI(S.schur(bulk, k2, npad, k2, k3, k0, k1, 0, 0));
+        if (two) { CKI(step_event(c, step, EV_B3A, &ev)); CK(cudaEventRecord(ev, bulk.st)); }
+        if (k3 >= npad) continue;
+        const int Mt = npad - k2, Nt = npad - k3;
+        const bool timed = c->trail_count < mplu_context::kMaxTrail;
+        if (timed) {
+            cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
+            if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
+            CKI(record_event(c, e0, bulk.st));
+        }
+        CKI(mark(c, 6000 + step, bulk.st));
+        CKI(S.schur(bulk, k2, npad, k3, npad, k0, k1, 0, 0));
+        CKI(mark(c, 7000 + step, bulk.st));
+        if (timed) {
+            CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], bulk.st));
+            c->trail_count++;
+            c->trail_flops += 2.0 * Mt * (double)Nt * NB;
+            c->trail_bytes += 8.0 * Mt * (double)Nt;
+        }
+    }
+    if (two) {
+        CK(cudaEventRecord(c->ev_join, c->side));
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     return 0;
 }
@@ -305,13 +453,14 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
 
     const bool use_graph = c->opts.use_graph != 0;
     mplu_context::GraphKey key{n, npad, c->opts.nb, c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
-                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->W};
+                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group, c->W};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
         c->gemm_launches = 0;
         c->kernel_launches = 2;  // first touch + anorm
         c->trail_count = 0;
         c->trail_flops = c->trail_bytes = 0;
+        c->mark_count = 0;
         if (use_graph) {
             if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
@@ -439,8 +588,10 @@ void mplu_default_options(mplu_options* o) {
     o->a_exp = 11;
     o->l_exp = 11;
     o->lookahead = 1;
-    o->side_sms = 24;
+    o->side_sms = 32;
     o->use_graph = 1;
+    o->pdl = 0;
+    o->group = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -480,6 +631,8 @@ void mplu_destroy(mplu_context* c) {
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_step) if (e) cudaEventDestroy(e);
+    for (auto& e : c->mark_ev) if (e) cudaEventDestroy(e);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -623,7 +776,11 @@ int mplu_diag_lu128(float* dW, long long ldw, float* dLinv, float* dUinv, void* 
     float* sc = nullptr;
     CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
     CK(cudaMalloc(&sc, 4 * sizeof(float)));
-    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, dLinv, dUinv, sc, 0, 0, nullptr, (cudaStream_t)stream);
+    // the kernel stores triangles only
+    CK(cudaMemsetAsync(dLinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream));
+    CK(cudaMemsetAsync(dUinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream));
+    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
+                            (cudaStream_t)stream);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(tmp16);
     cudaFree(sc);
@@ -638,12 +795,76 @@ int mplu_diag_lu128_timed(float* dW, long long ldw, float* dLinv, float* dUinv, 
     float* sc = nullptr;
     CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
     CK(cudaMalloc(&sc, 4 * sizeof(float)));
-    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, dLinv, dUinv, sc, 0, 0, nullptr, (cudaStream_t)stream,
-                            d_clocks);
+    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
+                            (cudaStream_t)stream, d_clocks);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(tmp16);
     cudaFree(sc);
     return rc;
+}
+
+// development aid: `reps` dependent launches of one GEMM shape (C += alpha*A*B, optional shadow) captured into a CUDA
+// graph and replayed; returns the average device time per launch in microseconds through *us_per_launch.
+int mplu_bench_gemm_chain(int variant, int M, int N, int K, int reps, int pdl, int shadow, int accumulate,
+                          int max_sms, float* us_per_launch) {
+    if (M <= 0 || N <= 0 || K <= 0 || K % 64 || reps <= 0 || !us_per_launch) return MPLU_E_ARG;
+    if (gemm_tc_init() != 0) return MPLU_E_TMAP;
+    uint16_t *A = nullptr, *B = nullptr, *H = nullptr;
+    float* Cm = nullptr;
+    CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)K * N * 2));
+    CK(cudaMalloc(&H, (size_t)M * N * 2)); CK(cudaMalloc(&Cm, (size_t)M * N * 4));
+    CK(cudaMemset(A, 0, (size_t)M * K * 2)); CK(cudaMemset(B, 0, (size_t)K * N * 2));
+    CK(cudaMemset(Cm, 0, (size_t)M * N * 4));
+    uint32_t abr, abc, bbr, bbc;
+    gemm_box_shapes(variant, &abr, &abc, &bbr, &bbc);
+    CUtensorMap tA, tB;
+    if (make_tmap_16bit(&tA, A, M, K, M, abr, abc)) return MPLU_E_TMAP;
+    if (make_tmap_16bit(&tB, B, K, N, K, bbr, bbc)) return MPLU_E_TMAP;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.C = Cm; p.ldc = M; p.Cin = accumulate ? Cm : nullptr; p.ldcin = M;
+    p.H = shadow ? H : nullptr; p.ldh = M; p.h_rows = M; p.h_cols = N; p.alpha = -1.f; p.hscale = 1.f; p.pdl = pdl;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    int rc = 0;
+    for (int i = 0; i < reps && !rc; ++i) rc = launch_gemm_tc(variant, &tA, &tB, p, max_sms, st);
+    CK(cudaStreamEndCapture(st, &graph));
+    if (rc) return rc;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaGraphLaunch(exec, st));
+    CK(cudaEventRecord(e0, st));
+    CK(cudaGraphLaunch(exec, st));
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *us_per_launch = 1e3f * ms / reps;
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaStreamDestroy(st); cudaFree(A); cudaFree(B); cudaFree(H); cudaFree(Cm);
+    return 0;
+}
+
+// development aid: switch timeline marks on (takes effect at the next schedule capture) / read them back as
+// (tag, milliseconds since the first mark) pairs after a synchronised factorization.  Returns the number of marks.
+void mplu_debug_marks_enable(mplu_context* c, int on) {
+    if (!c) return;
+    c->marks_on = on != 0;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+}
+int mplu_debug_timeline(mplu_context* c, int* tags, float* ms, int max) {
+    if (!c || !tags || !ms) return 0;
+    cudaStreamSynchronize(c->stream);
+    int n = c->mark_count < max ? c->mark_count : max;
+    for (int i = 0; i < n; ++i) {
+        tags[i] = c->mark_tag[i];
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], c->mark_ev[0], c->mark_ev[i]);
+    }
+    return n;
 }
 
 int mplu_residual(int n, const double* dA, long long lda, const double* dx, const double* db, double* dr,
