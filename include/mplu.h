@@ -27,7 +27,8 @@ enum {
     MPLU_E_TMAP = -4,       /* TMA descriptor encoding failed */
     MPLU_E_OVERFLOW = -5,   /* a 16-bit panel value left the fp16 range (factorization unusable) */
     MPLU_E_ZEROPIVOT = -6,  /* exact zero pivot met without pivoting */
-    MPLU_E_NOCONV = -7      /* refinement did not reach the tolerance in max_iters (x holds the last iterate) */
+    MPLU_E_NOCONV = -7,     /* refinement did not reach the tolerance in max_iters (x holds the last iterate) */
+    MPLU_E_NCCL = -8        /* NCCL missing (dlopen of libnccl.so.2 failed) or an NCCL call failed */
 };
 
 enum { MPLU_FP16 = 0, MPLU_BF16 = 1 };
@@ -126,6 +127,34 @@ int mplu_dgetf2_npv(int m, int n, double *d_panel, int ld, void *stream);
  * reference generator (matrix_generator.cpp:66) -- with, if `dominant`, the diagonal replaced by the column's
  * off-diagonal sum + 1.  db (optional) receives b = A * ones. */
 int mplu_generate(int n, unsigned long long seed, int dominant, double *dA, long long lda, double *db, void *stream);
+
+/* ---- 2D block-cyclic solver across the GPUs of one box (the reference is single-GPU,
+ * MPF.cu:77).  The n x n matrix is cut into nb x nb tiles, tile (I,J) lives on process (I mod P, J mod Q) of a
+ * P x Q grid, each process stores its tiles in ScaLAPACK local order (column-major mloc x nloc).  One process per
+ * GPU, NCCL over NVLink for the panel broadcasts and the refinement's reductions (libnccl.so.2 is loaded with dlopen
+ * on first use; single-GPU users never need it). */
+typedef struct mplu_dist mplu_dist;
+
+/* rank 0 creates the 128-byte NCCL unique id; the host program hands it to every rank (any transport) */
+int mplu_dist_unique_id(void *id128);
+/* this process becomes rank `rank` = p*Q + q of nranks = P*Q, computing on `device` */
+int mplu_dist_create(mplu_dist **out, int device, int rank, int nranks, int P, int Q, const void *id128);
+/* all P*Q logical ranks inside this process on one device, collectives as device copies (tests; no NCCL needed) */
+int mplu_dist_create_local(mplu_dist **out, int device, int P, int Q);
+void mplu_dist_destroy(mplu_dist *d);
+/* number of logical ranks hosted by this process (1 with NCCL, P*Q in local mode) */
+int mplu_dist_num_local(const mplu_dist *d);
+/* grid coordinates and local extents of logical rank i of this process for an n x n matrix tiled by nb */
+int mplu_dist_local_shape(const mplu_dist *d, int i, int n, int nb, int *p, int *q, long long *mloc, long long *nloc);
+/* factor + solve: dA[i] / lda[i] = local fp64 tiles of logical rank i (device), db[i] / dx[i] = FULL-length right-hand
+ * side and solution (device, replicated on every rank).  Requires n % nb == 0 and nb % 128 == 0. */
+int mplu_dist_gesv(mplu_dist *d, int n, int nb, const double *const *dA, const long long *lda,
+                   const double *const *db, double *const *dx, const mplu_options *opts, mplu_stats *stats);
+/* local fp32 L\U factors of logical rank i widened to fp64 (device, column-major mloc x nloc, leading dimension ld) */
+int mplu_dist_get_local_factors(mplu_dist *d, int i, double *dLU, long long ld);
+/* local tiles of the synthetic dominant system of mplu_generate for process (p,q), and the full b = A*1 */
+int mplu_generate_local(int n, unsigned long long seed, int nb, int P, int Q, int p, int q, double *dA_loc,
+                        long long lda, double *db_full, void *stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ GEMM_AUTO, GEMM_CG1, GEMM_CG2 = -1, 0, 1
 
 ERRORS = {
     0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "not factored", -4: "TMA descriptor encoding failed",
-    -5: "fp16 overflow in a panel", -6: "zero pivot", -7: "refinement did not converge",
+    -5: "fp16 overflow in a panel", -6: "zero pivot", -7: "refinement did not converge", -8: "NCCL error / unavailable",
 }
 
 
@@ -89,6 +89,20 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.mplu_hgetf2.restype = i
     lib.mplu_dgetf2_npv.argtypes = [i, i, vp, i, vp]
     lib.mplu_dgetf2_npv.restype = i
+    lib.mplu_dist_unique_id.argtypes = [vp]
+    lib.mplu_dist_create.argtypes = [C.POINTER(vp), i, i, i, i, i, vp]
+    lib.mplu_dist_create_local.argtypes = [C.POINTER(vp), i, i, i]
+    lib.mplu_dist_destroy.argtypes = [vp]
+    lib.mplu_dist_destroy.restype = None
+    lib.mplu_dist_num_local.argtypes = [vp]
+    lib.mplu_dist_local_shape.argtypes = [vp, i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(ll), C.POINTER(ll)]
+    lib.mplu_dist_gesv.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(ll), C.POINTER(vp), C.POINTER(vp),
+                                   C.POINTER(Options), C.POINTER(Stats)]
+    lib.mplu_dist_get_local_factors.argtypes = [vp, i, vp, ll]
+    lib.mplu_generate_local.argtypes = [i, C.c_ulonglong, i, i, i, i, i, vp, ll, vp, vp]
+    for name in ("mplu_dist_unique_id", "mplu_dist_create", "mplu_dist_create_local", "mplu_dist_num_local",
+                 "mplu_dist_local_shape", "mplu_dist_gesv", "mplu_dist_get_local_factors", "mplu_generate_local"):
+        getattr(lib, name).restype = i
     if path is None:
         _lib = lib
     return lib
@@ -172,6 +186,136 @@ class Solver:
         import torch
         LU = torch.empty(n, n, dtype=torch.float64, device="cuda").t()  # column-major storage
         _check(self._lib.mplu_get_factors(self._ctx, LU.data_ptr(), n, 1), "mplu_get_factors")
+        return LU
+
+
+# ---- 2D block-cyclic layout (host-side helpers; the same index maps as csrc/dist.cu) ------------------------------
+def grid_shape(nranks: int):
+    """P x Q process grid for `nranks` GPUs: the most square factorization with P <= Q (8 -> 2 x 4)."""
+    p = int(nranks ** 0.5)
+    while nranks % p:
+        p -= 1
+    return p, nranks // p
+
+
+def tiles_local(T: int, P: int, p: int) -> int:
+    """Number of the T tiles of one dimension that process p of P owns (tiles dealt round-robin)."""
+    return (T - p + P - 1) // P if p < T else 0
+
+
+def local_to_global(l: int, nb: int, P: int, p: int) -> int:
+    """Global row/column index of local index l on process p (ScaLAPACK local order)."""
+    return ((l // nb) * P + p) * nb + l % nb
+
+
+def global_to_local(g: int, nb: int, P: int):
+    """(owning process, local index) of global row/column g."""
+    t = g // nb
+    return t % P, (t // P) * nb + g % nb
+
+
+def scatter_block_cyclic(A, nb: int, P: int, Q: int):
+    """Split a global n x n array (numpy or torch) into the P*Q local arrays, row-major over (p, q)."""
+    n = A.shape[0]
+    T = n // nb
+    out = []
+    for p in range(P):
+        rows = [i for t in range(p, T, P) for i in range(t * nb, (t + 1) * nb)]
+        for q in range(Q):
+            cols = [j for t in range(q, T, Q) for j in range(t * nb, (t + 1) * nb)]
+            out.append(A[rows][:, cols])
+    return out
+
+
+def gather_block_cyclic(parts, n: int, nb: int, P: int, Q: int):
+    """Inverse of scatter_block_cyclic (numpy arrays)."""
+    import numpy as np
+    T = n // nb
+    A = np.zeros((n, n), dtype=parts[0].dtype)
+    for p in range(P):
+        rows = [i for t in range(p, T, P) for i in range(t * nb, (t + 1) * nb)]
+        for q in range(Q):
+            cols = [j for t in range(q, T, Q) for j in range(t * nb, (t + 1) * nb)]
+            if rows and cols:
+                A[np.ix_(rows, cols)] = parts[p * Q + q]
+    return A
+
+
+class DistSolver:
+    """Block-cyclic LU + IR over a P x Q process grid (csrc/dist.cu).
+
+    unique_id=None: "local" mode, all P*Q logical ranks live in this process on `device` (collectives are device
+    copies) -- used by the single-GPU tests.  Otherwise one rank of an NCCL communicator (one process per GPU)."""
+
+    def __init__(self, device: int, P: int, Q: int, rank: int | None = None, unique_id: bytes | None = None):
+        self._lib = load_library()
+        self._d = C.c_void_p()
+        self.P, self.Q = P, Q
+        if unique_id is None:
+            _check(self._lib.mplu_dist_create_local(C.byref(self._d), device, P, Q), "mplu_dist_create_local")
+        else:
+            buf = C.create_string_buffer(bytes(unique_id), 128)
+            _check(self._lib.mplu_dist_create(C.byref(self._d), device, rank, P * Q, P, Q, buf), "mplu_dist_create")
+        self.num_local = self._lib.mplu_dist_num_local(self._d)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(load_library().mplu_dist_unique_id(buf), "mplu_dist_unique_id")
+        return buf.raw
+
+    def close(self):
+        if self._d:
+            self._lib.mplu_dist_destroy(self._d)
+            self._d = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def local_shape(self, i, n, nb):
+        p, q, m, nn = C.c_int(), C.c_int(), C.c_longlong(), C.c_longlong()
+        _check(self._lib.mplu_dist_local_shape(self._d, i, n, nb, C.byref(p), C.byref(q), C.byref(m), C.byref(nn)),
+               "mplu_dist_local_shape")
+        return p.value, q.value, m.value, nn.value
+
+    def generate(self, n, nb, seed=1):
+        """Local tiles of the synthetic dominant system for every logical rank of this process + the full b."""
+        import torch
+        As, bs = [], []
+        for i in range(self.num_local):
+            p, q, m, nn = self.local_shape(i, n, nb)
+            A = torch.zeros(max(nn, 1), max(m, 1), dtype=torch.float64, device="cuda").t()  # column-major m x nn
+            b = torch.empty(n, dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            _check(self._lib.mplu_generate_local(n, seed, nb, self.P, self.Q, p, q, A.data_ptr(), A.stride(1),
+                                                 b.data_ptr(), None), "mplu_generate_local")
+            As.append(A)
+            bs.append(b)
+        torch.cuda.synchronize()
+        return As, bs
+
+    def gesv(self, n, nb, As, bs, opts=None, allow_noconv=False):
+        import torch
+        L = self.num_local
+        xs = [torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(L)]
+        pa = (C.c_void_p * L)(*[a.data_ptr() for a in As])
+        ld = (C.c_longlong * L)(*[a.stride(1) for a in As])
+        pb = (C.c_void_p * L)(*[b.data_ptr() for b in bs])
+        px = (C.c_void_p * L)(*[x.data_ptr() for x in xs])
+        st = Stats()
+        torch.cuda.synchronize()
+        _check(self._lib.mplu_dist_gesv(self._d, n, nb, pa, ld, pb, px, C.byref(opts) if opts else None, C.byref(st)),
+               "mplu_dist_gesv", allow=(-7,) if allow_noconv else ())
+        return xs, st
+
+    def local_factors(self, i, n, nb):
+        import torch
+        _, _, m, nn = self.local_shape(i, n, nb)
+        LU = torch.empty(max(nn, 1), max(m, 1), dtype=torch.float64, device="cuda").t()
+        _check(self._lib.mplu_dist_get_local_factors(self._d, i, LU.data_ptr(), LU.stride(1)), "mplu_dist_get_local_factors")
         return LU
 
 

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-I", str(ROOT / "include"),
 ]
 
-SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "generate.cu", "mpf_compat.cu"]
+SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "dist.cu", "generate.cu", "mpf_compat.cu"]
 
 
 def _nvcc() -> str:
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out.strip():
             print(out, file=sys.stderr)
     link = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-cudart", "static"]
+            "-cudart", "static", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

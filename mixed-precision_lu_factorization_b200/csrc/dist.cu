@@ -1,0 +1,888 @@
+// 2D block-cyclic mixed-precision LU + fp64 iterative refinement across the GPUs of one box.
+// The reference is single-GPU (cudaSetDevice(0), /root/reference/MPF.cu:77); this is the multi-GPU form of the same
+// hot path: tile (I,J) of the nb-tiled matrix lives on process (I mod P, J mod Q) in ScaLAPACK local order.
+//
+// Per step k (diagonal tile owner (k mod P, k mod Q)):
+//   chain lane  owner: GETRF of the nb x nb tile with merged inverses (lu.cu: getrf_resident_tile)
+//               broadcast inv(U11) down the owner's process column and inv(L11) along its process row; the factored
+//               tile and its fp32 block inverses go to every rank (they are replicated for the triangular solves)
+//               process column: L panel = A21 inv(U11) (one tcgen05 GEMM);  process row: U panel = inv(L11) A12
+//               broadcast the 16-bit L panel along process rows and the U panel along process columns (NCCL, NVLink)
+//   bulk lane   trailing update  A22 -= Lpanel * Upanel  on every rank; the next tile column / tile row first, so
+//               that step k+1's chain work overlaps the rest of update k (depth-1 look-ahead)
+// Refinement: every rank keeps full-length x, b, r; r = b - A x is a local fp64 GEMV + one all-reduce; the triangular
+// solves walk the tile rows (local fp32 GEMV + one nb-float all-reduce + the replicated diagonal tile's solve).
+//
+// One process hosts either ONE rank of an NCCL communicator (production: one process per GPU) or ALL P*Q logical
+// ranks on one device without NCCL ("local" mode: collectives become device copies) -- the same schedule code runs
+// in both, which is how the block-cyclic logic is tested on a single GPU.
+#include "lu_internal.h"
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+#include <new>
+
+using namespace mplu;
+using namespace mplu_detail;
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclFloat32 = 7, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    const char* names[] = {getenv("MPLU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return nullptr;
+#define LOADSYM(field, sym)                                            \
+    *(void**)(&api.field) = dlsym(api.handle, sym);                    \
+    if (!api.field) { api.handle = nullptr; return nullptr; }
+    LOADSYM(GetUniqueId, "ncclGetUniqueId")
+    LOADSYM(CommInitRank, "ncclCommInitRank")
+    LOADSYM(CommSplit, "ncclCommSplit")
+    LOADSYM(CommDestroy, "ncclCommDestroy")
+    LOADSYM(Broadcast, "ncclBroadcast")
+    LOADSYM(AllReduce, "ncclAllReduce")
+    LOADSYM(GroupStart, "ncclGroupStart")
+    LOADSYM(GroupEnd, "ncclGroupEnd")
+    LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+    return &api;
+}
+
+
+#define NK(expr)                                   \
+    do {                                           \
+        int _e = (expr);                           \
+        if (_e != ncclSuccess) return MPLU_E_NCCL; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ layout helpers
+// local tiles of a dimension with T tiles dealt round-robin to P processes
+inline int tiles_local(int T, int P, int p) { return p < T ? (T - p + P - 1) / P : 0; }
+// number of local tiles (of process p) whose global index is <= k / < k
+inline int cnt_le(int k, int P, int p) { return k >= p ? (k - p) / P + 1 : 0; }
+inline int cnt_lt(int k, int P, int p) { return k > p ? (k - 1 - p) / P + 1 : 0; }
+
+// ------------------------------------------------------------------------------------------------ kernels
+// W = fp32(A_loc) on the local mloc x nloc block, |A| max, partial row sums scattered to GLOBAL row positions.
+// grid (ceil(mloc/256), chunks); thread = one local row, loops over its chunk of local columns.
+__global__ void local_first_touch_kernel(const double* __restrict__ A, long long lda, int mloc, int nloc,
+                                         float* __restrict__ W, long long ldw, float* amax, double* rowsum_full,
+                                         int nb, int P, int p) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (nloc + gridDim.y - 1) / gridDim.y;
+    const int c0 = blockIdx.y * per, c1 = min(nloc, c0 + per);
+    float lmax = 0.f;
+    if (row < mloc) {
+        double rs = 0.0;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const double a = __ldg(A + row + (long long)c * lda);
+            const float w = static_cast<float>(a);
+            rs += fabs(a);
+            lmax = fmaxf(lmax, fabsf(w));
+            W[row + (long long)c * ldw] = w;
+        }
+        const long long grow = ((long long)(row / nb) * P + p) * nb + row % nb;
+        atomicAdd(rowsum_full + grow, rs);
+    }
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(lmax));
+}
+
+__global__ void max_abs_f64_kernel(const double* v, int n, double* out) {
+    double m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+// y_full[global row] += sum_{local cols in chunk} A_loc(row, c) * x[global col(c)]   (fp64, HBM-bound: 8 B / element)
+// grid (ceil(mloc/256), chunks); thread = 2 consecutive local rows (mloc, nb even).
+__global__ void __launch_bounds__(128)
+local_gemv_f64_kernel(const double* __restrict__ A, long long lda, int mloc, int nloc, const double* __restrict__ x,
+                      double* y_full, int nb, int P, int p, int Q, int q) {
+    extern __shared__ double xs[];
+    const int per = (nloc + gridDim.y - 1) / gridDim.y;
+    const int c0 = blockIdx.y * per, c1 = min(nloc, c0 + per);
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+        xs[c - c0] = x[((long long)(c / nb) * Q + q) * nb + c % nb];
+    __syncthreads();
+    const int r0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (r0 >= mloc) return;
+    const double* Ap = A + r0 + (long long)c0 * lda;
+    double a0 = 0.0, a1 = 0.0;
+    const int nc = c1 - c0;
+    const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    int c = 0;
+    if (vec) {
+        for (; c + 8 <= nc; c += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const double2*>(Ap + (long long)(c + u) * lda));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a0 = fma(v[u].x, xs[c + u], a0);
+                a1 = fma(v[u].y, xs[c + u], a1);
+            }
+        }
+    }
+    for (; c < nc; ++c) {
+        a0 = fma(__ldg(Ap + (long long)c * lda), xs[c], a0);
+        a1 = fma(__ldg(Ap + 1 + (long long)c * lda), xs[c], a1);
+    }
+    const long long grow = ((long long)(r0 / nb) * P + p) * nb + r0 % nb;
+    atomicAdd(y_full + grow, a0);
+    atomicAdd(y_full + grow + 1, a1);
+}
+
+// r = b - ax; norms[0] = max|r|, norms[1] = max|x|
+__global__ void residual_full_kernel(const double* __restrict__ b, const double* __restrict__ ax,
+                                     const double* __restrict__ x, double* __restrict__ r, int n, double* norms) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double rv = 0.0, xv = 0.0;
+    if (i < n) {
+        rv = b[i] - ax[i];
+        r[i] = rv;
+        rv = fabs(rv);
+        xv = fabs(x[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        rv = fmax(rv, __shfl_xor_sync(0xffffffffu, rv, o));
+        xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(reinterpret_cast<unsigned long long*>(&norms[0]), (unsigned long long)__double_as_longlong(rv));
+        atomicMax(reinterpret_cast<unsigned long long*>(&norms[1]), (unsigned long long)__double_as_longlong(xv));
+    }
+}
+
+// s[t] += sum_{c in [c_lo, c_hi)} W_loc(row0 + t, c) * v[global col(c)]     t < nb   (fp32 factors, fp32 vector)
+// grid (nb/256, chunks); thread = one row of the tile row.
+__global__ void tile_row_gemv_kernel(const float* __restrict__ W, long long ldw, int row0, int c_lo, int c_hi,
+                                     const float* __restrict__ v, float* s, int nb, int Q, int q) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int span = c_hi - c_lo;
+    const int per = (span + gridDim.y - 1) / gridDim.y;
+    const int a = c_lo + blockIdx.y * per, b = min(c_hi, a + per);
+    if (t >= nb || a >= b) return;
+    const float* wp = W + row0 + t;
+    float acc0 = 0.f, acc1 = 0.f;
+    int c = a;
+    for (; c + 1 < b; c += 2) {
+        const float v0 = __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb);
+        const float v1 = __ldg(v + ((long long)((c + 1) / nb) * Q + q) * nb + (c + 1) % nb);
+        acc0 = fmaf(__ldcs(wp + (long long)c * ldw), v0, acc0);
+        acc1 = fmaf(__ldcs(wp + (long long)(c + 1) * ldw), v1, acc1);
+    }
+    if (c < b) acc0 = fmaf(__ldcs(wp + (long long)c * ldw), __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb), acc0);
+    atomicAdd(s + t, acc0 + acc1);
+}
+
+// forward: rhs64[t] = r[k nb + t] - s[t];  backward: yk[t] -= s[t]
+__global__ void tile_rhs_fwd_kernel(const double* __restrict__ r, const float* __restrict__ s, double* rhs64, int nb) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nb) rhs64[t] = r[t] - (double)s[t];
+}
+__global__ void tile_rhs_bwd_kernel(const float* __restrict__ y, const float* __restrict__ s, float* out, int nb) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nb) out[t] = y[t] - s[t];
+}
+// x (+)= d
+__global__ void apply_correction_kernel(const float* __restrict__ d, double* x, int n, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = accumulate ? x[i] + (double)d[i] : (double)d[i];
+}
+// local-mode collectives
+__global__ void sum_into_f32_kernel(float* dst, const float* src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void sum_into_f64_kernel(double* dst, const double* src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void max_into_f32_kernel(float* dst, const float* src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = fmaxf(dst[i], src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ rank state
+struct DRank {
+    int p = 0, q = 0;
+    mplu_context* ctx = nullptr;   // options / status / small device words for the GEMM launches of this rank
+    mplu_context* dctx = nullptr;  // nb x nb context that factors diagonal tiles
+    cudaStream_t chain = nullptr, bulk = nullptr;
+    cudaEvent_t ev_tmp = nullptr, ev_chain = nullptr, ev_bulk = nullptr, ev_e1 = nullptr, ev_panel[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    int mt = 0, nt = 0;
+    long long mloc = 0, nloc = 0;
+    const double* A = nullptr;
+    long long lda = 0;
+    float* W = nullptr;
+    uint16_t* Wh = nullptr;
+    uint16_t* Lp[2] = {nullptr, nullptr};
+    uint16_t* Up[2] = {nullptr, nullptr};
+    uint16_t* InvL[2] = {nullptr, nullptr};
+    uint16_t* InvU[2] = {nullptr, nullptr};
+    float* tsc[2] = {nullptr, nullptr};  // {s_Linv, 1/s_Linv, s_Uinv, 1/s_Uinv} of the step's tile
+    float* Dw = nullptr;    // T x (nb x nb) replicated factored diagonal tiles
+    float* Dl32 = nullptr;  // T x nb/128 x (128 x 128) replicated fp32 inverses of their diagonal blocks
+    float* Du32 = nullptr;
+    Operand16 opWh, opLp[2], opUp[2], opInvL[2], opInvU[2];
+    // refinement vectors (full length, replicated)
+    double *r = nullptr, *ax = nullptr, *rowsum = nullptr, *norms = nullptr, *rhs64 = nullptr, *anorm = nullptr;
+    float *yv = nullptr, *xv = nullptr, *sv = nullptr, *tmpf = nullptr;
+    unsigned* ready = nullptr;
+};
+
+}  // namespace
+
+struct mplu_dist {
+    int device = 0;
+    int P = 1, Q = 1;
+    bool local_mode = true;
+    int rank = 0, nranks = 1;
+    ncclComm_t world = nullptr, rowc = nullptr, colc = nullptr;
+    NcclApi* nccl = nullptr;
+    std::vector<DRank> ranks;  // logical ranks hosted by this process (1 with NCCL, P*Q in local mode)
+    int n = 0, nb = 0, T = 0;
+    mplu_options opts{};
+    int num_sms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    int gemm_launches = 0, kernel_launches = 0;
+};
+
+namespace {
+
+void free_rank_work(DRank& r) {
+    cudaFree(r.W); cudaFree(r.Wh);
+    for (int i = 0; i < 2; ++i) { cudaFree(r.Lp[i]); cudaFree(r.Up[i]); cudaFree(r.InvL[i]); cudaFree(r.InvU[i]); cudaFree(r.tsc[i]); }
+    cudaFree(r.Dw); cudaFree(r.Dl32); cudaFree(r.Du32);
+    cudaFree(r.r); cudaFree(r.ax); cudaFree(r.rowsum); cudaFree(r.norms); cudaFree(r.rhs64); cudaFree(r.anorm);
+    cudaFree(r.yv); cudaFree(r.xv); cudaFree(r.sv); cudaFree(r.tmpf); cudaFree(r.ready);
+    r.W = nullptr; r.Wh = nullptr;
+    for (int i = 0; i < 2; ++i) { r.Lp[i] = r.Up[i] = r.InvL[i] = r.InvU[i] = nullptr; r.tsc[i] = nullptr; }
+    r.Dw = r.Dl32 = r.Du32 = nullptr;
+    r.r = r.ax = r.rowsum = r.norms = r.rhs64 = r.anorm = nullptr;
+    r.yv = r.xv = r.sv = r.tmpf = nullptr;
+    r.ready = nullptr;
+}
+
+int alloc_rank_work(mplu_dist* d, DRank& r) {
+    const int n = d->n, nb = d->nb, T = d->T;
+    free_rank_work(r);
+    r.mt = tiles_local(T, d->P, r.p);
+    r.nt = tiles_local(T, d->Q, r.q);
+    r.mloc = (long long)r.mt * nb;
+    r.nloc = (long long)r.nt * nb;
+    const size_t ml = (size_t)(r.mloc > 0 ? r.mloc : nb), nl = (size_t)(r.nloc > 0 ? r.nloc : nb);
+    CK(cudaMalloc(&r.W, ml * nl * sizeof(float)));
+    CK(cudaMalloc(&r.Wh, ml * nl * sizeof(uint16_t)));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&r.Lp[i], ml * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&r.Up[i], nl * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&r.InvL[i], (size_t)nb * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&r.InvU[i], (size_t)nb * nb * sizeof(uint16_t)));
+        CK(cudaMalloc(&r.tsc[i], 4 * sizeof(float)));
+    }
+    CK(cudaMalloc(&r.Dw, (size_t)T * nb * nb * sizeof(float)));
+    CK(cudaMalloc(&r.Dl32, (size_t)n * kDiagBlock * sizeof(float)));
+    CK(cudaMalloc(&r.Du32, (size_t)n * kDiagBlock * sizeof(float)));
+    CK(cudaMalloc(&r.r, n * sizeof(double)));
+    CK(cudaMalloc(&r.ax, n * sizeof(double)));
+    CK(cudaMalloc(&r.rowsum, n * sizeof(double)));
+    CK(cudaMalloc(&r.norms, 2 * sizeof(double)));
+    CK(cudaMalloc(&r.anorm, 2 * sizeof(double)));
+    CK(cudaMalloc(&r.rhs64, nb * sizeof(double)));
+    CK(cudaMalloc(&r.yv, n * sizeof(float)));
+    CK(cudaMalloc(&r.xv, n * sizeof(float)));
+    CK(cudaMalloc(&r.sv, nb * sizeof(float)));
+    CK(cudaMalloc(&r.tmpf, nb * sizeof(float)));
+    CK(cudaMalloc(&r.ready, sizeof(unsigned)));
+    CKI(make_operand(&r.opWh, r.Wh, ml, nl, ml));
+    for (int i = 0; i < 2; ++i) {
+        CKI(make_operand(&r.opInvL[i], r.InvL[i], nb, nb, nb));
+        CKI(make_operand(&r.opInvU[i], r.InvU[i], nb, nb, nb));
+        CKI(make_operand(&r.opUp[i], r.Up[i], nb, nl, nb));
+    }
+    // the nb x nb factorization context
+    r.dctx->opts = d->opts;
+    r.dctx->opts.nb = nb;
+    r.dctx->opts.lookahead = 0;
+    r.dctx->opts.use_graph = 0;
+    CKI(ensure_work(r.dctx, nb));
+    r.ctx->opts = d->opts;
+    return 0;
+}
+
+DRank* find_rank(mplu_dist* d, int p, int q) {
+    for (auto& r : d->ranks)
+        if (r.p == p && r.q == q) return &r;
+    return nullptr;
+}
+
+// ---- collectives.  scope: 0 = world, 1 = process row `line` (ranks (line, *)), 2 = process column `line`.
+// `root` = the q (row scope) / p (column scope) / world rank p*Q+q of the sender.  get(rank) returns the rank's buffer;
+// stream_of(rank) the stream the operation is ordered on.
+template <class GetBuf, class GetStream>
+int bcast(mplu_dist* d, int scope, int line, int root, size_t bytes, GetBuf get, GetStream stream_of) {
+    if (bytes == 0) return 0;
+    if (!d->local_mode) {
+        DRank& r = d->ranks[0];
+        if ((scope == 1 && r.p != line) || (scope == 2 && r.q != line)) return 0;
+        ncclComm_t comm = scope == 0 ? d->world : (scope == 1 ? d->rowc : d->colc);
+        void* buf = get(r);
+        NK(d->nccl->Broadcast(buf, buf, bytes, ncclUint8, root, comm, stream_of(r)));
+        return 0;
+    }
+    DRank* src = nullptr;
+    for (auto& r : d->ranks) {
+        const bool in = scope == 0 || (scope == 1 && r.p == line) || (scope == 2 && r.q == line);
+        if (!in) continue;
+        const int id = scope == 0 ? r.p * d->Q + r.q : (scope == 1 ? r.q : r.p);
+        if (id == root) src = &r;
+    }
+    if (!src) return MPLU_E_ARG;
+    CK(cudaEventRecord(src->ev_tmp, stream_of(*src)));
+    for (auto& r : d->ranks) {
+        const bool in = scope == 0 || (scope == 1 && r.p == line) || (scope == 2 && r.q == line);
+        if (!in || &r == src) continue;
+        CK(cudaStreamWaitEvent(stream_of(r), src->ev_tmp, 0));
+        CK(cudaMemcpyAsync(get(r), get(*src), bytes, cudaMemcpyDeviceToDevice, stream_of(r)));
+        // the sender must not overwrite its buffer before the copy ran
+        CK(cudaEventRecord(r.ev_tmp, stream_of(r)));
+        CK(cudaStreamWaitEvent(stream_of(*src), r.ev_tmp, 0));
+    }
+    return 0;
+}
+
+// in-place all-reduce over the world; dtype: 0 f32 sum, 1 f64 sum, 2 f32 max
+template <class GetBuf, class GetStream>
+int allreduce(mplu_dist* d, int dtype, size_t count, GetBuf get, GetStream stream_of) {
+    if (count == 0) return 0;
+    if (!d->local_mode) {
+        DRank& r = d->ranks[0];
+        void* buf = get(r);
+        NK(d->nccl->AllReduce(buf, buf, count, dtype == 1 ? ncclFloat64 : ncclFloat32, dtype == 2 ? ncclMax : ncclSum,
+                              d->world, stream_of(r)));
+        return 0;
+    }
+    if (d->ranks.size() == 1) return 0;
+    DRank& r0 = d->ranks[0];
+    cudaStream_t s0 = stream_of(r0);
+    const int blocks = (int)((count + 255) / 256);
+    for (size_t i = 1; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        CK(cudaEventRecord(r.ev_tmp, stream_of(r)));
+        CK(cudaStreamWaitEvent(s0, r.ev_tmp, 0));
+        if (dtype == 0) sum_into_f32_kernel<<<blocks, 256, 0, s0>>>((float*)get(r0), (const float*)get(r), count);
+        else if (dtype == 1) sum_into_f64_kernel<<<blocks, 256, 0, s0>>>((double*)get(r0), (const double*)get(r), count);
+        else max_into_f32_kernel<<<blocks, 256, 0, s0>>>((float*)get(r0), (const float*)get(r), count);
+    }
+    CK(cudaEventRecord(r0.ev_tmp, s0));
+    const size_t bytes = count * (dtype == 1 ? 8 : 4);
+    for (size_t i = 1; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        CK(cudaStreamWaitEvent(stream_of(r), r0.ev_tmp, 0));
+        CK(cudaMemcpyAsync(get(r), get(r0), bytes, cudaMemcpyDeviceToDevice, stream_of(r)));
+        CK(cudaEventRecord(r.ev_tmp, stream_of(r)));
+        CK(cudaStreamWaitEvent(s0, r.ev_tmp, 0));
+    }
+    return 0;
+}
+
+// ---- factorization schedule ------------------------------------------------------------------------------------
+int enqueue_dist_factorization(mplu_dist* d) {
+    const int nb = d->nb, T = d->T, P = d->P, Q = d->Q;
+    const int bf16 = d->opts.precision == MPLU_BF16;
+    int side_sms = d->opts.side_sms > 0 ? d->opts.side_sms : 32;
+    side_sms -= side_sms % 2;
+    const bool two = d->opts.lookahead != 0 && side_sms >= 2 && side_sms <= d->num_sms - 16;
+    auto chain_of = [](DRank& r) { return r.chain; };
+
+    // first touch: fp32 working copy, global |A| max, global row sums -> ||A||_inf; scales; full 16-bit shadow
+    for (auto& r : d->ranks) {
+        CK(cudaMemsetAsync(r.ctx->status, 0, sizeof(int), r.chain));
+        CK(cudaMemsetAsync(r.dctx->status, 0, sizeof(int), r.chain));
+        CK(cudaMemsetAsync(r.ctx->amax, 0, sizeof(float), r.chain));
+        CK(cudaMemsetAsync(r.rowsum, 0, d->n * sizeof(double), r.chain));
+        if (r.mloc > 0 && r.nloc > 0) {
+            dim3 grid((unsigned)((r.mloc + 255) / 256), 32);
+            local_first_touch_kernel<<<grid, 256, 0, r.chain>>>(r.A, r.lda, (int)r.mloc, (int)r.nloc, r.W, r.mloc,
+                                                                 r.ctx->amax, r.rowsum, nb, P, r.p);
+        }
+    }
+    CKI(allreduce(d, 2, 1, [](DRank& r) { return (void*)r.ctx->amax; }, chain_of));
+    CKI(allreduce(d, 1, (size_t)d->n, [](DRank& r) { return (void*)r.rowsum; }, chain_of));
+    for (auto& r : d->ranks) {
+        CK(cudaMemsetAsync(r.anorm, 0, 2 * sizeof(double), r.chain));
+        max_abs_f64_kernel<<<64, 256, 0, r.chain>>>(r.rowsum, d->n, r.anorm);
+        CKI(launch_scales(r.ctx->amax, r.ctx->scales, d->opts.a_exp, d->opts.l_exp, bf16, r.chain));
+        CK(cudaMemcpyAsync(r.dctx->scales, r.ctx->scales, SC_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, r.chain));
+        if (r.mloc > 0 && r.nloc > 0)
+            CKI(launch_shadow_cast(r.W, r.mloc, r.Wh, r.mloc, (int)r.mloc, (int)r.nloc, r.ctx->scales + SC_A, bf16,
+                                   r.ctx->status, r.chain));
+        CK(cudaEventRecord(r.ev_chain, r.chain));
+        CK(cudaStreamWaitEvent(r.bulk, r.ev_chain, 0));
+        d->kernel_launches += 4;
+    }
+
+    for (int k = 0; k < T; ++k) {
+        const int pk = k % P, qk = k % Q, b = k & 1;
+        // ---- chain lane: GETRF on the owner
+        for (auto& r : d->ranks) {
+            if (k > 0) CK(cudaStreamWaitEvent(r.chain, r.ev_e1, 0));  // tile column / row k carry update k-1
+            if (r.p != pk || r.q != qk) continue;
+            const long long ik = k / P, jk = k / Q;
+            mplu_context* dc = r.dctx;
+            float* tile = r.W + ik * nb + jk * nb * r.mloc;
+            CK(cudaMemcpy2DAsync(dc->W, (size_t)nb * sizeof(float), tile, (size_t)r.mloc * sizeof(float),
+                                 (size_t)nb * sizeof(float), nb, cudaMemcpyDeviceToDevice, r.chain));
+            dc->gemm_launches = dc->kernel_launches = 0;
+            dc->opts.max_sms = two ? side_sms : 0;
+            CKI(getrf_resident_tile(dc, r.chain));
+            d->gemm_launches += dc->gemm_launches;
+            d->kernel_launches += dc->kernel_launches + 1;
+            CK(cudaMemcpy2DAsync(tile, (size_t)r.mloc * sizeof(float), dc->W, (size_t)nb * sizeof(float),
+                                 (size_t)nb * sizeof(float), nb, cudaMemcpyDeviceToDevice, r.chain));
+            // publish into this rank's slots of the replicated stores and the step's inverse buffers
+            CK(cudaMemcpyAsync(r.Dw + (size_t)k * nb * nb, dc->W, (size_t)nb * nb * sizeof(float), cudaMemcpyDeviceToDevice, r.chain));
+            CK(cudaMemcpyAsync(r.Dl32 + (size_t)k * nb * kDiagBlock, dc->Linv32, (size_t)nb * kDiagBlock * sizeof(float), cudaMemcpyDeviceToDevice, r.chain));
+            CK(cudaMemcpyAsync(r.Du32 + (size_t)k * nb * kDiagBlock, dc->Uinv32, (size_t)nb * kDiagBlock * sizeof(float), cudaMemcpyDeviceToDevice, r.chain));
+            CK(cudaMemcpy2DAsync(r.InvL[b], (size_t)nb * 2, dc->Linv16, (size_t)dc->cap_nb * 2, (size_t)nb * 2, nb, cudaMemcpyDeviceToDevice, r.chain));
+            CK(cudaMemcpy2DAsync(r.InvU[b], (size_t)nb * 2, dc->Uinv16, (size_t)dc->cap_nb * 2, (size_t)nb * 2, nb, cudaMemcpyDeviceToDevice, r.chain));
+            CK(cudaMemcpyAsync(r.tsc[b], dc->inv_scales, 4 * sizeof(float), cudaMemcpyDeviceToDevice, r.chain));
+        }
+        // ---- broadcasts of the tile's results
+        const int owner = pk * Q + qk;
+        if (!d->local_mode) NK(d->nccl->GroupStart());
+        CKI(bcast(d, 0, 0, owner, (size_t)nb * nb * sizeof(float), [&](DRank& r) { return (void*)(r.Dw + (size_t)k * nb * nb); }, chain_of));
+        CKI(bcast(d, 0, 0, owner, (size_t)nb * kDiagBlock * sizeof(float), [&](DRank& r) { return (void*)(r.Dl32 + (size_t)k * nb * kDiagBlock); }, chain_of));
+        CKI(bcast(d, 0, 0, owner, (size_t)nb * kDiagBlock * sizeof(float), [&](DRank& r) { return (void*)(r.Du32 + (size_t)k * nb * kDiagBlock); }, chain_of));
+        CKI(bcast(d, 0, 0, owner, 4 * sizeof(float), [&](DRank& r) { return (void*)r.tsc[b]; }, chain_of));
+        CKI(bcast(d, 1, pk, qk, (size_t)nb * nb * 2, [&](DRank& r) { return (void*)r.InvL[b]; }, chain_of));
+        CKI(bcast(d, 2, qk, pk, (size_t)nb * nb * 2, [&](DRank& r) { return (void*)r.InvU[b]; }, chain_of));
+        if (!d->local_mode) NK(d->nccl->GroupEnd());
+        if (k == T - 1) break;
+
+        // ---- panel solves on the owner's process column / row, into compact panel buffers
+        for (auto& r : d->ranks) {
+            const int ilo = cnt_le(k, P, r.p), jlo = cnt_le(k, Q, r.q);
+            const long long rows = r.mloc - (long long)ilo * nb, cols = r.nloc - (long long)jlo * nb;
+            const Lane ln{r.chain, two ? 2 * side_sms : 0};
+            if (k >= 2) CK(cudaStreamWaitEvent(r.chain, r.ev_panel[b], 0));  // update k-2 has consumed buffers b
+            if (rows > 0) CKI(make_operand(&r.opLp[b], r.Lp[b], (uint64_t)rows, (uint64_t)nb, (uint64_t)rows));
+            if (r.q == qk && rows > 0) {
+                const long long jk = k / Q;
+                GemmCall g{&r.opWh, (int)(ilo * nb), (int)(jk * nb), &r.opInvU[b], 0, 0, (int)rows, nb, nb,
+                           r.W + (long long)ilo * nb + jk * nb * r.mloc, r.mloc, false,
+                           r.Lp[b], rows, (int)rows, nb, 1.f, r.ctx->scales + SC_A_INV, r.tsc[b] + 3, r.ctx->scales + SC_L};
+                CKI(run_gemm(r.ctx, ln, g));
+            }
+            if (r.p == pk && cols > 0) {
+                const long long ik = k / P;
+                GemmCall g{&r.opInvL[b], 0, 0, &r.opWh, (int)(ik * nb), (int)(jlo * nb), nb, (int)cols, nb,
+                           r.W + ik * nb + (long long)jlo * nb * r.mloc, r.mloc, false,
+                           r.Up[b] + (long long)jlo * nb * nb, nb, nb, (int)cols, 1.f, r.tsc[b] + 1,
+                           r.ctx->scales + SC_A_INV, r.ctx->scales + SC_A};
+                CKI(run_gemm(r.ctx, ln, g));
+            }
+        }
+        // ---- panel broadcasts: L panel along each process row (root column qk), U panel along each process column
+        if (!d->local_mode) NK(d->nccl->GroupStart());
+        for (int p = 0; p < P; ++p) {
+            const long long rows = (long long)(tiles_local(T, P, p) - cnt_le(k, P, p)) * nb;
+            if (rows > 0)
+                CKI(bcast(d, 1, p, qk, (size_t)rows * nb * 2, [&](DRank& r) { return (void*)r.Lp[b]; }, chain_of));
+        }
+        for (int q = 0; q < Q; ++q) {
+            const int jlo = cnt_le(k, Q, q);
+            const long long cols = (long long)(tiles_local(T, Q, q) - jlo) * nb;
+            if (cols > 0)
+                CKI(bcast(d, 2, q, pk, (size_t)cols * nb * 2,
+                          [&](DRank& r) { return (void*)(r.Up[b] + (long long)jlo * nb * nb); }, chain_of));
+        }
+        if (!d->local_mode) NK(d->nccl->GroupEnd());
+
+        // ---- trailing update: next tile column and tile row first (16-bit shadows for step k+1), then the rest
+        const int pn = (k + 1) % P, qn = (k + 1) % Q;
+        for (auto& r : d->ranks) {
+            const int ilo = cnt_le(k, P, r.p), jlo = cnt_le(k, Q, r.q);
+            const long long rows = r.mloc - (long long)ilo * nb, cols = r.nloc - (long long)jlo * nb;
+            CK(cudaEventRecord(r.ev_chain, r.chain));
+            CK(cudaStreamWaitEvent(r.bulk, r.ev_chain, 0));
+            if (rows <= 0 || cols <= 0) {
+                CK(cudaEventRecord(r.ev_e1, r.bulk));
+                CK(cudaEventRecord(r.ev_panel[b], r.bulk));
+                continue;
+            }
+            const Lane lb{r.bulk, two ? d->num_sms - side_sms : 0};
+            const float* alpha = r.ctx->scales + SC_NEG_LA_INV;
+            const float* hs = r.ctx->scales + SC_A;
+            auto update = [&](long long r0, long long r1, long long c0, long long c1, bool shadow) {
+                // local rows [r0, r1), local columns [c0, c1)
+                if (r1 <= r0 || c1 <= c0) return 0;
+                GemmCall g{&r.opLp[b], (int)(r0 - (long long)ilo * nb), 0, &r.opUp[b], 0, (int)c0,
+                           (int)(r1 - r0), (int)(c1 - c0), nb, r.W + r0 + c0 * r.mloc, r.mloc, true,
+                           r.Wh + r0 + c0 * r.mloc, r.mloc, shadow ? (int)(r1 - r0) : 0, shadow ? (int)(c1 - c0) : 0,
+                           1.f, alpha, nullptr, hs};
+                return run_gemm(r.ctx, lb, g);
+            };
+            const long long R0 = (long long)ilo * nb, C0 = (long long)jlo * nb;
+            long long c_rest = C0, r_rest = R0;
+            if (r.q == qn) {  // owns tile column k+1: first local tile column of the region
+                CKI(update(R0, r.mloc, C0, C0 + nb, true));
+                c_rest = C0 + nb;
+            }
+            if (r.p == pn) {  // owns tile row k+1
+                CKI(update(R0, R0 + nb, c_rest, r.nloc, true));
+                r_rest = R0 + nb;
+            }
+            CK(cudaEventRecord(r.ev_e1, r.bulk));
+            CKI(update(r_rest, r.mloc, c_rest, r.nloc, false));
+            CK(cudaEventRecord(r.ev_panel[b], r.bulk));
+        }
+    }
+    for (auto& r : d->ranks) {
+        CK(cudaEventRecord(r.ev_bulk, r.bulk));
+        CK(cudaStreamWaitEvent(r.chain, r.ev_bulk, 0));
+        d->gemm_launches += r.ctx->gemm_launches;
+        d->kernel_launches += r.ctx->kernel_launches;
+        r.ctx->gemm_launches = r.ctx->kernel_launches = 0;
+    }
+    return 0;
+}
+
+// ---- refinement ------------------------------------------------------------------------------------------------
+// ax = A x over all ranks; r = b - ax; norms
+int enqueue_residual(mplu_dist* d, const std::vector<const double*>& b, const std::vector<double*>& x) {
+    auto chain_of = [](DRank& r) { return r.chain; };
+    for (size_t i = 0; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        CK(cudaMemsetAsync(r.ax, 0, d->n * sizeof(double), r.chain));
+        if (r.mloc > 0 && r.nloc > 0) {
+            const int chunks = (int)std::max<long long>(16, (r.nloc + 4095) / 4096);
+            const int per = (int)((r.nloc + chunks - 1) / chunks);
+            dim3 grid((unsigned)((r.mloc / 2 + 127) / 128), chunks);
+            local_gemv_f64_kernel<<<grid, 128, per * sizeof(double), r.chain>>>(r.A, r.lda, (int)r.mloc, (int)r.nloc, x[i],
+                                                                                 r.ax, d->nb, d->P, r.p, d->Q, r.q);
+        }
+        d->kernel_launches += 2;
+    }
+    CKI(allreduce(d, 1, (size_t)d->n, [](DRank& r) { return (void*)r.ax; }, chain_of));
+    for (size_t i = 0; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        CK(cudaMemsetAsync(r.norms, 0, 2 * sizeof(double), r.chain));
+        residual_full_kernel<<<(d->n + 255) / 256, 256, 0, r.chain>>>(b[i], r.ax, x[i], r.r, d->n, r.norms);
+    }
+    return (int)cudaGetLastError();
+}
+
+// solve L U dvec = rhs with the distributed fp32 factors; result (float, full length) in r.xv of every rank
+int enqueue_lu_solve(mplu_dist* d, const std::vector<const double*>& rhs) {
+    const int nb = d->nb, T = d->T, P = d->P, Q = d->Q;
+    auto chain_of = [](DRank& r) { return r.chain; };
+    auto sv_of = [](DRank& r) { return (void*)r.sv; };
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int kk = 0; kk < T; ++kk) {
+            const int k = sweep == 0 ? kk : T - 1 - kk;
+            const int pk = k % P;
+            for (size_t i = 0; i < d->ranks.size(); ++i) {
+                DRank& r = d->ranks[i];
+                CK(cudaMemsetAsync(r.sv, 0, nb * sizeof(float), r.chain));
+                if (r.p == pk && r.nloc > 0 && kk > 0) {
+                    // forward: local tile columns with J < k; backward: J > k
+                    const int c_lo = sweep == 0 ? 0 : cnt_le(k, Q, r.q) * nb;
+                    const int c_hi = sweep == 0 ? cnt_lt(k, Q, r.q) * nb : (int)r.nloc;
+                    if (c_hi > c_lo) {
+                        const int span = c_hi - c_lo;
+                        const int chunks = span >= 8192 ? 32 : (span >= 1024 ? 8 : 1);
+                        dim3 grid((nb + 255) / 256, chunks);
+                        tile_row_gemv_kernel<<<grid, 256, 0, r.chain>>>(r.W, r.mloc, (k / P) * nb, c_lo, c_hi,
+                                                                         sweep == 0 ? r.yv : r.xv, r.sv, nb, Q, r.q);
+                        d->kernel_launches++;
+                    }
+                }
+            }
+            if (kk > 0) CKI(allreduce(d, 0, (size_t)nb, sv_of, chain_of));
+            for (size_t i = 0; i < d->ranks.size(); ++i) {
+                DRank& r = d->ranks[i];
+                const float* Dk = r.Dw + (size_t)k * nb * nb;
+                const float* Li = r.Dl32 + (size_t)k * nb * kDiagBlock;
+                const float* Ui = r.Du32 + (size_t)k * nb * kDiagBlock;
+                if (sweep == 0) {
+                    tile_rhs_fwd_kernel<<<(nb + 255) / 256, 256, 0, r.chain>>>(rhs[i] + (size_t)k * nb, r.sv, r.rhs64, nb);
+                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, r.rhs64, r.yv + (size_t)k * nb, nullptr, nullptr, nullptr,
+                                        r.ready, 1, r.chain));
+                } else {
+                    tile_rhs_bwd_kernel<<<(nb + 255) / 256, 256, 0, r.chain>>>(r.yv + (size_t)k * nb, r.sv, r.tmpf, nb);
+                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, nullptr, r.tmpf, r.xv + (size_t)k * nb, nullptr, nullptr,
+                                        r.ready, 2, r.chain));
+                }
+                d->kernel_launches += 3;
+            }
+        }
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int mplu_dist_unique_id(void* id128) {
+    NcclApi* api = nccl_api();
+    if (!api || !id128) return MPLU_E_NCCL;
+    ncclUniqueId id;
+    NK(api->GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
+    d->device = device;
+    d->P = P;
+    d->Q = Q;
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
+    mplu_default_options(&d->opts);
+    CK(cudaEventCreate(&d->ev0)); CK(cudaEventCreate(&d->ev1)); CK(cudaEventCreate(&d->ev2));
+    for (auto& r : d->ranks) {
+        CKI(mplu_create(&r.ctx, device));
+        CKI(mplu_create(&r.dctx, device));
+        r.chain = r.ctx->stream;
+        r.bulk = r.ctx->side;
+        cudaEvent_t* evs[] = {&r.ev_tmp, &r.ev_chain, &r.ev_bulk, &r.ev_e1, &r.ev_panel[0], &r.ev_panel[1]};
+        for (auto e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int mplu_dist_create(mplu_dist** out, int device, int rank, int nranks, int P, int Q, const void* id128) {
+    if (!out || P <= 0 || Q <= 0 || P * Q != nranks || rank < 0 || rank >= nranks || !id128) return MPLU_E_ARG;
+    NcclApi* api = nccl_api();
+    if (!api) return MPLU_E_NCCL;
+    mplu_dist* d = new (std::nothrow) mplu_dist();
+    if (!d) return MPLU_E_ARG;
+    d->local_mode = false;
+    d->nccl = api;
+    d->rank = rank;
+    d->nranks = nranks;
+    d->ranks.resize(1);
+    d->ranks[0].p = rank / Q;
+    d->ranks[0].q = rank % Q;
+    int rc = dist_create_common(d, device, P, Q);
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NK(api->CommInitRank(&d->world, nranks, id, rank));
+    // process row p: ranks (p, *) ordered by q; process column q: ranks (*, q) ordered by p
+    NK(api->CommSplit(d->world, d->ranks[0].p, d->ranks[0].q, &d->rowc, nullptr));
+    NK(api->CommSplit(d->world, d->ranks[0].q, d->ranks[0].p, &d->colc, nullptr));
+    *out = d;
+    return 0;
+}
+
+int mplu_dist_create_local(mplu_dist** out, int device, int P, int Q) {
+    if (!out || P <= 0 || Q <= 0 || P * Q > 64) return MPLU_E_ARG;
+    mplu_dist* d = new (std::nothrow) mplu_dist();
+    if (!d) return MPLU_E_ARG;
+    d->local_mode = true;
+    d->nranks = P * Q;
+    d->ranks.resize((size_t)P * Q);
+    for (int p = 0; p < P; ++p)
+        for (int q = 0; q < Q; ++q) {
+            d->ranks[(size_t)p * Q + q].p = p;
+            d->ranks[(size_t)p * Q + q].q = q;
+        }
+    int rc = dist_create_common(d, device, P, Q);
+    if (rc) return rc;
+    *out = d;
+    return 0;
+}
+
+void mplu_dist_destroy(mplu_dist* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    for (auto& r : d->ranks) {
+        free_rank_work(r);
+        cudaEvent_t evs[] = {r.ev_tmp, r.ev_chain, r.ev_bulk, r.ev_e1, r.ev_panel[0], r.ev_panel[1]};
+        for (auto e : evs) if (e) cudaEventDestroy(e);
+        mplu_destroy(r.ctx);
+        mplu_destroy(r.dctx);
+    }
+    if (d->nccl) {
+        if (d->rowc) d->nccl->CommDestroy(d->rowc);
+        if (d->colc) d->nccl->CommDestroy(d->colc);
+        if (d->world) d->nccl->CommDestroy(d->world);
+    }
+    cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1); cudaEventDestroy(d->ev2);
+    delete d;
+}
+
+int mplu_dist_num_local(const mplu_dist* d) { return d ? (int)d->ranks.size() : 0; }
+
+// local tile-row / tile-column counts of logical rank i of this process for an n x n matrix tiled by nb
+int mplu_dist_local_shape(const mplu_dist* d, int i, int n, int nb, int* p, int* q, long long* mloc, long long* nloc) {
+    if (!d || i < 0 || i >= (int)d->ranks.size() || nb <= 0 || n % nb) return MPLU_E_ARG;
+    const DRank& r = d->ranks[i];
+    const int T = n / nb;
+    if (p) *p = r.p;
+    if (q) *q = r.q;
+    if (mloc) *mloc = (long long)tiles_local(T, d->P, r.p) * nb;
+    if (nloc) *nloc = (long long)tiles_local(T, d->Q, r.q) * nb;
+    return 0;
+}
+
+// factor + solve.  dA[i] / lda[i]: local block-cyclic fp64 tiles of logical rank i (column-major, mloc x nloc);
+// db[i], dx[i]: full-length (n) right-hand side and solution on every rank.  n % nb == 0, nb % 128 == 0.
+int mplu_dist_gesv(mplu_dist* d, int n, int nb, const double* const* dA, const long long* lda,
+                   const double* const* db, double* const* dx, const mplu_options* opts, mplu_stats* stats) {
+    if (!d || n <= 0 || nb < kDiagBlock || nb % kDiagBlock || n % nb || !dA || !lda || !db || !dx) return MPLU_E_ARG;
+    CK(cudaSetDevice(d->device));
+    if (opts) d->opts = *opts;
+    d->opts.nb = nb;
+    const bool realloc = (n != d->n || nb != d->nb);
+    d->n = n;
+    d->nb = nb;
+    d->T = n / nb;
+    d->gemm_launches = d->kernel_launches = 0;
+    std::vector<const double*> bv, rv;
+    std::vector<double*> xv;
+    for (size_t i = 0; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        if (realloc) CKI(alloc_rank_work(d, r));
+        r.ctx->opts = d->opts;
+        r.dctx->opts.precision = d->opts.precision;
+        r.dctx->opts.gemm_variant = d->opts.gemm_variant;
+        r.dctx->opts.group = d->opts.group;
+        r.dctx->opts.pdl = d->opts.pdl;
+        r.A = dA[i];
+        r.lda = lda[i];
+        if (r.mloc > 0 && lda[i] < r.mloc) return MPLU_E_ARG;
+        bv.push_back(db[i]);
+        xv.push_back(dx[i]);
+        rv.push_back(r.r);
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    DRank& r0 = d->ranks[0];
+    CK(cudaEventRecord(d->ev0, r0.chain));
+    CKI(enqueue_dist_factorization(d));
+    CK(cudaEventRecord(d->ev1, r0.chain));
+
+    // ||b||_inf, first solve x = (LU)^-1 b
+    for (size_t i = 0; i < d->ranks.size(); ++i) {
+        DRank& r = d->ranks[i];
+        max_abs_f64_kernel<<<64, 256, 0, r.chain>>>(bv[i], n, r.anorm + 1);
+    }
+    CKI(enqueue_lu_solve(d, bv));
+    for (size_t i = 0; i < d->ranks.size(); ++i)
+        apply_correction_kernel<<<(n + 255) / 256, 256, 0, d->ranks[i].chain>>>(d->ranks[i].xv, xv[i], n, 0);
+
+    double h_norms[2] = {0, 0}, h_an[2] = {0, 0};
+    const double eps = 2.220446049250313e-16 / 2.0;
+    int iters = 0, converged = 0;
+    double first_be = -1.0;
+    const int max_iters = d->opts.max_iters > 0 ? d->opts.max_iters : 30;
+    std::vector<const double*> xc(xv.begin(), xv.end());
+    for (;;) {
+        CKI(enqueue_residual(d, bv, xv));
+        // every process takes the decision from its own (identical) copy of the norms
+        CK(cudaMemcpyAsync(h_norms, r0.norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, r0.chain));
+        if (first_be < 0) CK(cudaMemcpyAsync(h_an, r0.anorm, 2 * sizeof(double), cudaMemcpyDeviceToHost, r0.chain));
+        for (auto& r : d->ranks) CK(cudaStreamSynchronize(r.chain));
+        const double be = h_norms[0] / (h_an[0] * h_norms[1] + h_an[1]);
+        if (first_be < 0) first_be = be;
+        const double thresh = d->opts.tol > 0 ? d->opts.tol * h_an[0] * h_norms[1]
+                                               : h_norms[1] * h_an[0] * eps * std::sqrt((double)n);
+        if (!(h_norms[0] == h_norms[0])) break;
+        if (h_norms[0] <= thresh) { converged = 1; break; }
+        if (iters >= max_iters) break;
+        CKI(enqueue_lu_solve(d, rv));
+        for (size_t i = 0; i < d->ranks.size(); ++i)
+            apply_correction_kernel<<<(n + 255) / 256, 256, 0, d->ranks[i].chain>>>(d->ranks[i].xv, xv[i], n, 1);
+        ++iters;
+    }
+    CK(cudaEventRecord(d->ev2, r0.chain));
+    CK(cudaEventSynchronize(d->ev2));
+    int h_status = 0;
+    for (auto& r : d->ranks) {
+        int s1 = 0, s2 = 0;
+        CK(cudaMemcpy(&s1, r.ctx->status, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&s2, r.dctx->status, sizeof(int), cudaMemcpyDeviceToHost));
+        h_status |= s1 | s2;
+    }
+    if (stats) {
+        stats->n = n;
+        stats->iters = iters;
+        stats->converged = converged;
+        stats->status_bits = h_status;
+        stats->anorm_inf = h_an[0];
+        stats->bnorm_inf = h_an[1];
+        stats->xnorm_inf = h_norms[1];
+        stats->rnorm_inf = h_norms[0];
+        stats->backward_error = h_norms[0] / (h_an[0] * h_norms[1] + h_an[1]);
+        stats->first_backward_error = first_be;
+        stats->gemm_launches = d->gemm_launches;
+        stats->kernel_launches = d->kernel_launches;
+        cudaEventElapsedTime(&stats->factor_ms, d->ev0, d->ev1);
+        cudaEventElapsedTime(&stats->solve_ms, d->ev1, d->ev2);
+        cudaEventElapsedTime(&stats->total_ms, d->ev0, d->ev2);
+    }
+    if (converged) return 0;
+    if (h_status & 1) return MPLU_E_OVERFLOW;
+    if (h_status & 2) return MPLU_E_ZEROPIVOT;
+    return MPLU_E_NOCONV;
+}
+
+// Copy logical rank i's local fp32 factors (L\U in block-cyclic local order, mloc x nloc) widened to fp64.
+int mplu_dist_get_local_factors(mplu_dist* d, int i, double* dLU, long long ld) {
+    if (!d || i < 0 || i >= (int)d->ranks.size() || !dLU) return MPLU_E_ARG;
+    DRank& r = d->ranks[i];
+    if (ld < r.mloc) return MPLU_E_ARG;
+    std::vector<float> h((size_t)r.mloc * r.nloc);
+    CK(cudaMemcpy(h.data(), r.W, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<double> hd(h.size());
+    for (size_t e = 0; e < h.size(); ++e) hd[e] = h[e];
+    CK(cudaMemcpy2D(dLU, (size_t)ld * sizeof(double), hd.data(), (size_t)r.mloc * sizeof(double),
+                    (size_t)r.mloc * sizeof(double), (size_t)r.nloc, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // extern "C"

@@ -115,14 +115,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __global__ void __launch_bounds__(TSV_THREADS)
 lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
                 const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
-                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready) {
+                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end) {
     extern __shared__ __align__(16) float s_inv[];  // 128 x 128 inverse of the step's diagonal block
     __shared__ __align__(16) float s_part[8][DBS];
     __shared__ float s_acc[DBS];
     const int tid = threadIdx.x;
     const int rg = tid & 31, cg = tid >> 5;  // rows 4rg.., columns 16cg.. of a tile
     unsigned seen = 0;
-    for (int s = blockIdx.x; s < 2 * nblk; s += gridDim.x) {
+    // steps [s_begin, s_end): [0, 2*nblk) = both sweeps; [0, nblk) forward only; [nblk, 2*nblk) backward only (its
+    // right-hand side is then read from ysol and *ready must start at nblk)
+    for (int s = s_begin + blockIdx.x; s < s_end; s += gridDim.x) {
         const bool back = s >= nblk;
         const int t = back ? s - nblk : s;         // tiles in this block row
         const int i = back ? nblk - 1 - t : t;     // block row
@@ -217,8 +219,18 @@ int launch_residual(const double* A, long long lda, int n, const double* x, cons
     return (int)cudaGetLastError();
 }
 
+namespace {
+__global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+}  // namespace
+
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st) {
+    return launch_lu_sweep(W, ldw, n, npad, Linv32, Uinv32, rhs, y, y + npad, d_out, x_accum, ready, 0, st);
+}
+
+int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
+                    const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
+                    int mode, cudaStream_t st) {
     static int max_grid = 0;
     if (!max_grid) {
         cudaError_t e = cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSV_SMEM_BYTES);
@@ -232,13 +244,12 @@ int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float*
         max_grid = sms * per_sm;
     }
     int nblk = npad / DBS;
-    float* ysol = y;
-    float* xsol = y + npad;  // caller provides 2*npad floats
-    cudaError_t e = cudaMemsetAsync(ready, 0, sizeof(unsigned), st);
-    if (e != cudaSuccess) return (int)e;
+    int s_begin = mode == 2 ? nblk : 0, s_end = mode == 1 ? nblk : 2 * nblk;
+    set_u32_kernel<<<1, 1, 0, st>>>(ready, (unsigned)s_begin);
     const int grid = nblk < max_grid ? nblk : max_grid;
     void* args[] = {(void*)&W, (void*)&ldw, (void*)&n, (void*)&nblk, (void*)&Linv32, (void*)&Uinv32, (void*)&rhs,
-                    (void*)&ysol, (void*)&xsol, (void*)&d_out, (void*)&x_accum, (void*)&ready};
+                    (void*)&ysol, (void*)&xsol, (void*)&d_out, (void*)&x_accum, (void*)&ready, (void*)&s_begin,
+                    (void*)&s_end};
     return (int)cudaLaunchCooperativeKernel((void*)lu_solve_kernel, dim3(grid), dim3(TSV_THREADS), args, TSV_SMEM_BYTES,
                                             st);
 }

@@ -43,4 +43,10 @@ int launch_residual(const double* A, long long lda, int n, const double* x, cons
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st);
 
+// One sweep only: mode 0 = both (as launch_lu_solve), 1 = forward (L y = rhs, y -> ysol), 2 = backward (U x = ysol,
+// x -> xsol); used tile by tile by the block-cyclic solver.
+int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
+                    const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
+                    int mode, cudaStream_t st);
+
 }  // namespace mplu

@@ -32,8 +32,9 @@ def test_reference_symbols_keep_their_mangled_names(mplu):
 
 def test_default_options(mplu):
     o = mplu.default_options()
-    assert (o.precision, o.nb, o.max_iters, o.a_exp, o.l_exp) == (0, 1024, 30, 11, 11)
-    assert o.nb % 128 == 0
+    # nb = 0 means "by n" (resolved at factorization time); pdl is off by default (measured slower)
+    assert (o.precision, o.nb, o.max_iters, o.a_exp, o.l_exp) == (0, 0, 30, 11, 11)
+    assert (o.lookahead, o.use_graph, o.pdl, o.group) == (1, 1, 0, 1) and o.side_sms % 2 == 0
 
 
 def test_no_device_is_reported_not_crashed(mplu):
