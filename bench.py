@@ -108,7 +108,7 @@ def run_reference(args):
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mplu_oracle as orc
-    n = args.n
+    n = args.n or 32768
     n_cpu = min(n, 8192)
     cpu = cpu_lapack_baseline(n_cpu)
     line = dict(impl="reference", metric=METRIC, unit="TFLOP/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
@@ -162,12 +162,104 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_distributed(args, m, pk, rank, world, local):
+    """N > 1: ONE n x n system, 2D block-cyclic over a P x Q grid (one process per GPU, NCCL over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    n = args.n or 131072
+    nb = args.nb or 2048
+    P, Q = m.grid_shape(world)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(m.DistSolver.unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    ds = m.DistSolver(local, P, Q, rank=rank, unique_id=bytes(uid.cpu().tolist()))
+    opts = m.default_options(precision=1 if args.precision == "bf16" else 0)
+    As, bs = ds.generate(n, nb, seed=1)
+    p, q, mloc, nloc = ds.local_shape(0, n, nb)
+    for _ in range(args.warmup):
+        xs, st = ds.gesv(n, nb, As, bs, opts)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = tr_ms = tr_fl = tr_by = 0.0
+    tr_n = launches = iters = 0
+    worst_be = 0.0
+    for _ in range(args.steps):
+        xs, st = ds.gesv(n, nb, As, bs, opts)  # returns after its own stream sync; device time in st.total_ms
+        dev_ms += st.total_ms
+        tr_ms += st.trailing_ms; tr_fl += st.trailing_flops; tr_by += st.trailing_bytes; tr_n += st.trailing_launches
+        launches += st.kernel_launches
+        iters = max(iters, st.iters)
+        worst_be = max(worst_be, st.backward_error)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([dev_ms / args.steps, wall_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, wall_max = float(t[0].item()), float(t[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    fwd_err = float((xs[0] - 1).abs().max().item())
+
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hA = torch.empty(max(nloc, 1), max(mloc, 1), dtype=torch.float64, pin_memory=True)
+            hA.copy_(As[0].t())
+            hb = bs[0].cpu().pin_memory()
+            hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            del As
+            torch.cuda.empty_cache()
+            ds.gesv_host(n, nb, [hA.t()], [hb], [hx], opts)  # warm-up (staging allocation)
+            torch.cuda.synchronize()
+            dist.barrier()
+            k_e2e = max(1, min(args.steps, 2))
+            t1 = time.perf_counter()
+            for _ in range(k_e2e):
+                st_h = ds.gesv_host(n, nb, [hA.t()], [hb], [hx], opts)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t1) / k_e2e
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = dict(value=flops(n) / float(tt.item()) / 1e12, unit="TFLOP/s", h2d_bytes_per_step=8 * n * n + 8 * n * world,
+                       d2h_bytes_per_step=8 * n * world, ms_per_step=1e3 * float(tt.item()), h2d_ms=st_h.h2d_ms,
+                       max_abs_err=float((hx - 1).abs().max().item()))
+        except Exception as ex:  # e.g. not enough pinnable host memory for the local tiles
+            e2e = dict(value=None, unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0, skipped=repr(ex)[:200])
+    if rank == 0:
+        value = flops(n) / (ms_max * 1e-3) / 1e12
+        ach = (tr_fl / (tr_ms * 1e-3) / 1e12) if tr_ms > 0 else None
+        line = dict(metric=METRIC, value=value, unit="TFLOP/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_max, wall_ms_per_step=wall_max, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype=args.precision + " operands, f32 accumulate, f64 refinement", data="synthetic",
+                    config=dict(workload=f"n={n} 2D block-cyclic LU+IR across {world} B200 (BASELINE.json configs[3]); one system, "
+                                         f"value = 2/3 n^3 / time", n=n, nb=nb, rhs=1, grid=f"{P}x{Q}",
+                                matrix="column-diagonally-dominant, values k/10 (reference generator distribution), seed=1",
+                                l2_policy="inputs larger than L2 (local A is %.1f GiB per GPU)" % (8.0 * mloc * nloc / 2 ** 30),
+                                parallelism=f"2D block-cyclic {P}x{Q}, NCCL panel broadcasts, depth-1 look-ahead"),
+                    ir_iters=iters, backward_error=worst_be, max_abs_err=fwd_err, factor_ms=st.factor_ms, solve_ms=st.solve_ms,
+                    gpu_launches=launches, clocks=clocks, e2e=e2e,
+                    roofline=dict(bound="tensor", kernel="gemm_tc_kernel (rank-nb trailing update, rank 0's launches)", achieved=ach,
+                                  peak=pk["tc_sustained"], unit="TFLOP/s", frac=(ach / pk["tc_sustained"]) if ach else None,
+                                  peak_kind=f"bf16_tflops_sustained ({pk['src']}); burst {pk['tc_burst']}", launches=tr_n,
+                                  avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
+                                  share_of_step=(tr_ms / args.steps / ms_max) if ms_max > 0 else None, traffic=None),
+                    headline_frac_of_peak=value / world / pk["tc_sustained"])
+        print(json.dumps(line), flush=True)
+    ds.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--n", type=int, default=0, help="matrix order (default: 32768 on 1 GPU, 131072 block-cyclic on N > 1)")
     ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default for this n)")
     ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
     ap.add_argument("--impl", choices=["mplu", "reference"], default="mplu")
@@ -195,15 +287,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = importlib.import_module(PKG_NAME)
     pk = peaks()
-    n = args.n
+    if world > 1:
+        return run_distributed(args, m, pk, rank, world, local)
+    n = args.n or 32768
     opts = m.default_options(precision=1 if args.precision == "bf16" else 0)
     if args.nb:
         opts.nb = args.nb
-    elif n >= 16384:
-        opts.nb = 2048
 
-    # N > 1: the ranks solve independent systems (replicas, weak scaling) -- the 2D block-cyclic single-system path
-    # is described in DESIGN.md section 7 and not yet wired into bench.py.
     solver = m.Solver(local)
     A, b = m.generate(n, seed=1 + rank)
     x = torch.empty(n, dtype=torch.float64, device="cuda")

@@ -150,6 +150,10 @@ int mplu_dist_local_shape(const mplu_dist *d, int i, int n, int nb, int *p, int 
  * side and solution (device, replicated on every rank).  Requires n % nb == 0 and nb % 128 == 0. */
 int mplu_dist_gesv(mplu_dist *d, int n, int nb, const double *const *dA, const long long *lda,
                    const double *const *db, double *const *dx, const mplu_options *opts, mplu_stats *stats);
+/* the same solve from HOST buffers (local tiles hA[i], full hb[i]; full hx[i] out): H2D / D2H inside the call */
+int mplu_dist_gesv_host(mplu_dist *d, int n, int nb, const double *const *hA, const long long *lda,
+                        const double *const *hb, double *const *hx, const mplu_options *opts, mplu_stats *stats);
+void mplu_dist_release_staging(mplu_dist *d);
 /* local fp32 L\U factors of logical rank i widened to fp64 (device, column-major mloc x nloc, leading dimension ld) */
 int mplu_dist_get_local_factors(mplu_dist *d, int i, double *dLU, long long ld);
 /* local tiles of the synthetic dominant system of mplu_generate for process (p,q), and the full b = A*1 */

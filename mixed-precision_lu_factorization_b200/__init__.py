@@ -98,6 +98,10 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.mplu_dist_local_shape.argtypes = [vp, i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(ll), C.POINTER(ll)]
     lib.mplu_dist_gesv.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(ll), C.POINTER(vp), C.POINTER(vp),
                                    C.POINTER(Options), C.POINTER(Stats)]
+    lib.mplu_dist_gesv_host.argtypes = lib.mplu_dist_gesv.argtypes
+    lib.mplu_dist_gesv_host.restype = i
+    lib.mplu_dist_release_staging.argtypes = [vp]
+    lib.mplu_dist_release_staging.restype = None
     lib.mplu_dist_get_local_factors.argtypes = [vp, i, vp, ll]
     lib.mplu_generate_local.argtypes = [i, C.c_ulonglong, i, i, i, i, i, vp, ll, vp, vp]
     for name in ("mplu_dist_unique_id", "mplu_dist_create", "mplu_dist_create_local", "mplu_dist_num_local",
@@ -310,6 +314,21 @@ class DistSolver:
         _check(self._lib.mplu_dist_gesv(self._d, n, nb, pa, ld, pb, px, C.byref(opts) if opts else None, C.byref(st)),
                "mplu_dist_gesv", allow=(-7,) if allow_noconv else ())
         return xs, st
+
+    def gesv_host(self, n, nb, hAs, hbs, hxs, opts=None, allow_noconv=False):
+        """hAs: host (ideally pinned) torch tensors with column-major local tiles; hbs / hxs: full host vectors."""
+        L = self.num_local
+        pa = (C.c_void_p * L)(*[a.data_ptr() for a in hAs])
+        ld = (C.c_longlong * L)(*[a.stride(1) for a in hAs])
+        pb = (C.c_void_p * L)(*[b.data_ptr() for b in hbs])
+        px = (C.c_void_p * L)(*[x.data_ptr() for x in hxs])
+        st = Stats()
+        _check(self._lib.mplu_dist_gesv_host(self._d, n, nb, pa, ld, pb, px, C.byref(opts) if opts else None,
+                                             C.byref(st)), "mplu_dist_gesv_host", allow=(-7,) if allow_noconv else ())
+        return st
+
+    def release_staging(self):
+        self._lib.mplu_dist_release_staging(self._d)
 
     def local_factors(self, i, n, nb):
         import torch

@@ -191,25 +191,40 @@ __global__ void residual_full_kernel(const double* __restrict__ b, const double*
 }
 
 // s[t] += sum_{c in [c_lo, c_hi)} W_loc(row0 + t, c) * v[global col(c)]     t < nb   (fp32 factors, fp32 vector)
-// grid (nb/256, chunks); thread = one row of the tile row.
-__global__ void tile_row_gemv_kernel(const float* __restrict__ W, long long ldw, int row0, int c_lo, int c_hi,
-                                     const float* __restrict__ v, float* s, int nb, int Q, int q) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int span = c_hi - c_lo;
-    const int per = (span + gridDim.y - 1) / gridDim.y;
-    const int a = c_lo + blockIdx.y * per, b = min(c_hi, a + per);
-    if (t >= nb || a >= b) return;
-    const float* wp = W + row0 + t;
-    float acc0 = 0.f, acc1 = 0.f;
-    int c = a;
-    for (; c + 1 < b; c += 2) {
-        const float v0 = __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb);
-        const float v1 = __ldg(v + ((long long)((c + 1) / nb) * Q + q) * nb + (c + 1) % nb);
-        acc0 = fmaf(__ldcs(wp + (long long)c * ldw), v0, acc0);
-        acc1 = fmaf(__ldcs(wp + (long long)(c + 1) * ldw), v1, acc1);
+// HBM-bound (4 bytes per element of the tile row).  grid (nb/512, ceil(span/128)); block 128 threads; a thread owns 4
+// consecutive rows (128-bit loads, 8 columns in flight) of a 128-column chunk and adds its partial sums atomically.
+__global__ void __launch_bounds__(128)
+tile_row_gemv_kernel(const float* __restrict__ W, long long ldw, int row0, int c_lo, int c_hi,
+                     const float* __restrict__ v, float* s, int nb, int Q, int q) {
+    __shared__ float vs[128];
+    const int a = c_lo + blockIdx.y * 128, b = min(c_hi, a + 128);
+    for (int c = a + threadIdx.x; c < b; c += 128) vs[c - a] = __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb);
+    __syncthreads();
+    const int t = 4 * (blockIdx.x * 128 + threadIdx.x);
+    if (t >= nb) return;
+    const float4* wp = reinterpret_cast<const float4*>(W + row0 + t + (long long)a * ldw);
+    const long long ld4 = ldw / 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nc = b - a;
+    int c = 0;
+    for (; c + 8 <= nc; c += 8) {
+        float4 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldcs(wp + (long long)(c + u) * ld4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float x = vs[c + u];
+            acc.x = fmaf(w[u].x, x, acc.x); acc.y = fmaf(w[u].y, x, acc.y);
+            acc.z = fmaf(w[u].z, x, acc.z); acc.w = fmaf(w[u].w, x, acc.w);
+        }
     }
-    if (c < b) acc0 = fmaf(__ldcs(wp + (long long)c * ldw), __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb), acc0);
-    atomicAdd(s + t, acc0 + acc1);
+    for (; c < nc; ++c) {
+        const float4 w = __ldcs(wp + (long long)c * ld4);
+        const float x = vs[c];
+        acc.x = fmaf(w.x, x, acc.x); acc.y = fmaf(w.y, x, acc.y);
+        acc.z = fmaf(w.z, x, acc.z); acc.w = fmaf(w.w, x, acc.w);
+    }
+    atomicAdd(s + t, acc.x); atomicAdd(s + t + 1, acc.y); atomicAdd(s + t + 2, acc.z); atomicAdd(s + t + 3, acc.w);
 }
 
 // forward: rhs64[t] = r[k nb + t] - s[t];  backward: yk[t] -= s[t]
@@ -284,6 +299,14 @@ struct mplu_dist {
     int num_sms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     int gemm_launches = 0, kernel_launches = 0;
+    // device timing of the first hosted rank's trailing updates (the dominant kernel), like mplu_context::trail_ev
+    std::vector<cudaEvent_t> trail_ev;
+    int trail_count = 0;
+    double trail_flops = 0, trail_bytes = 0;
+    // staging of the host-buffer variant (one entry per logical rank)
+    std::vector<double*> stA, stb, stx;
+    std::vector<size_t> stA_cap;
+    int st_n = 0;
 };
 
 namespace {
@@ -425,6 +448,23 @@ int allreduce(mplu_dist* d, int dtype, size_t count, GetBuf get, GetStream strea
     return 0;
 }
 
+// SMs for the chain lane at a step whose local trailing block is rows x cols: the smallest budget whose estimated chain
+// time (diagonal-tile GETRF: latency part + work part, the two panel GEMMs, the panel broadcasts) stays under 3/4 of the
+// estimated trailing-update time on the remaining SMs -- early steps of large matrices give almost the whole GPU to
+// the update, late steps fall back to the configured maximum.  Rates: measured on B200.
+int pick_side_sms(const mplu_dist* d, long long rows, long long cols, int max_side) {
+    const double nb = d->nb, sms = d->num_sms;
+    const double upd_ms = 2.0 * rows * cols * nb / 1.15e15 * 1e3;
+    const double f = nb / 2048.0;
+    const double bcast_ms = (rows + cols) * nb * 2.0 / 3.0e11 * 1e3;
+    for (int s = 8; s < max_side; s += 8) {
+        const double getrf_ms = 1.0 * f + 0.3 * f * f * f * 32.0 / s;
+        const double panel_ms = 2.0 * nb * nb * (rows + cols) / (s * 9.4e12 * 0.6) * 1e3;
+        if (getrf_ms + panel_ms + bcast_ms <= 0.75 * upd_ms * sms / (sms - s)) return s;
+    }
+    return max_side;
+}
+
 // ---- factorization schedule ------------------------------------------------------------------------------------
 int enqueue_dist_factorization(mplu_dist* d) {
     const int nb = d->nb, T = d->T, P = d->P, Q = d->Q;
@@ -461,8 +501,14 @@ int enqueue_dist_factorization(mplu_dist* d) {
         d->kernel_launches += 4;
     }
 
+    std::vector<int> side(d->ranks.size(), side_sms);
     for (int k = 0; k < T; ++k) {
         const int pk = k % P, qk = k % Q, b = k & 1;
+        for (size_t i = 0; i < d->ranks.size(); ++i) {
+            DRank& r = d->ranks[i];
+            const long long rows = r.mloc - (long long)cnt_le(k, P, r.p) * nb, cols = r.nloc - (long long)cnt_le(k, Q, r.q) * nb;
+            side[i] = (two && d->opts.side_sms >= 0) ? pick_side_sms(d, rows > 0 ? rows : 0, cols > 0 ? cols : 0, side_sms) : side_sms;
+        }
         // ---- chain lane: GETRF on the owner
         for (auto& r : d->ranks) {
             if (k > 0) CK(cudaStreamWaitEvent(r.chain, r.ev_e1, 0));  // tile column / row k carry update k-1
@@ -473,7 +519,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
             CK(cudaMemcpy2DAsync(dc->W, (size_t)nb * sizeof(float), tile, (size_t)r.mloc * sizeof(float),
                                  (size_t)nb * sizeof(float), nb, cudaMemcpyDeviceToDevice, r.chain));
             dc->gemm_launches = dc->kernel_launches = 0;
-            dc->opts.max_sms = two ? side_sms : 0;
+            dc->opts.max_sms = two ? side[&r - &d->ranks[0]] : 0;
             CKI(getrf_resident_tile(dc, r.chain));
             d->gemm_launches += dc->gemm_launches;
             d->kernel_launches += dc->kernel_launches + 1;
@@ -503,7 +549,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
         for (auto& r : d->ranks) {
             const int ilo = cnt_le(k, P, r.p), jlo = cnt_le(k, Q, r.q);
             const long long rows = r.mloc - (long long)ilo * nb, cols = r.nloc - (long long)jlo * nb;
-            const Lane ln{r.chain, two ? 2 * side_sms : 0};
+            const Lane ln{r.chain, two ? side[&r - &d->ranks[0]] : 0};
             if (k >= 2) CK(cudaStreamWaitEvent(r.chain, r.ev_panel[b], 0));  // update k-2 has consumed buffers b
             if (rows > 0) CKI(make_operand(&r.opLp[b], r.Lp[b], (uint64_t)rows, (uint64_t)nb, (uint64_t)rows));
             if (r.q == qk && rows > 0) {
@@ -550,7 +596,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
                 CK(cudaEventRecord(r.ev_panel[b], r.bulk));
                 continue;
             }
-            const Lane lb{r.bulk, two ? d->num_sms - side_sms : 0};
+            const Lane lb{r.bulk, two ? d->num_sms - side[&r - &d->ranks[0]] : 0};
             const float* alpha = r.ctx->scales + SC_NEG_LA_INV;
             const float* hs = r.ctx->scales + SC_A;
             auto update = [&](long long r0, long long r1, long long c0, long long c1, bool shadow) {
@@ -573,7 +619,22 @@ int enqueue_dist_factorization(mplu_dist* d) {
                 r_rest = R0 + nb;
             }
             CK(cudaEventRecord(r.ev_e1, r.bulk));
+            const bool timed = (&r == &d->ranks[0]) && r.mloc > r_rest && r.nloc > c_rest;
+            if (timed) {
+                if ((int)d->trail_ev.size() < 2 * (d->trail_count + 1)) {
+                    cudaEvent_t a, bb;
+                    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&bb));
+                    d->trail_ev.push_back(a); d->trail_ev.push_back(bb);
+                }
+                CK(cudaEventRecord(d->trail_ev[2 * d->trail_count], r.bulk));
+            }
             CKI(update(r_rest, r.mloc, c_rest, r.nloc, false));
+            if (timed) {
+                CK(cudaEventRecord(d->trail_ev[2 * d->trail_count + 1], r.bulk));
+                d->trail_count++;
+                d->trail_flops += 2.0 * (double)(r.mloc - r_rest) * (double)(r.nloc - c_rest) * nb;
+                d->trail_bytes += 8.0 * (double)(r.mloc - r_rest) * (double)(r.nloc - c_rest);
+            }
             CK(cudaEventRecord(r.ev_panel[b], r.bulk));
         }
     }
@@ -630,9 +691,8 @@ int enqueue_lu_solve(mplu_dist* d, const std::vector<const double*>& rhs) {
                     const int c_hi = sweep == 0 ? cnt_lt(k, Q, r.q) * nb : (int)r.nloc;
                     if (c_hi > c_lo) {
                         const int span = c_hi - c_lo;
-                        const int chunks = span >= 8192 ? 32 : (span >= 1024 ? 8 : 1);
-                        dim3 grid((nb + 255) / 256, chunks);
-                        tile_row_gemv_kernel<<<grid, 256, 0, r.chain>>>(r.W, r.mloc, (k / P) * nb, c_lo, c_hi,
+                        dim3 grid((nb + 511) / 512, (span + 127) / 128);
+                        tile_row_gemv_kernel<<<grid, 128, 0, r.chain>>>(r.W, r.mloc, (k / P) * nb, c_lo, c_hi,
                                                                          sweep == 0 ? r.yv : r.xv, r.sv, nb, Q, r.q);
                         d->kernel_launches++;
                     }
@@ -736,6 +796,8 @@ int mplu_dist_create_local(mplu_dist** out, int device, int P, int Q) {
     return 0;
 }
 
+void mplu_dist_release_staging(mplu_dist* d);
+
 void mplu_dist_destroy(mplu_dist* d) {
     if (!d) return;
     cudaSetDevice(d->device);
@@ -752,6 +814,8 @@ void mplu_dist_destroy(mplu_dist* d) {
         if (d->colc) d->nccl->CommDestroy(d->colc);
         if (d->world) d->nccl->CommDestroy(d->world);
     }
+    mplu_dist_release_staging(d);
+    for (auto e : d->trail_ev) cudaEventDestroy(e);
     cudaEventDestroy(d->ev0); cudaEventDestroy(d->ev1); cudaEventDestroy(d->ev2);
     delete d;
 }
@@ -783,6 +847,8 @@ int mplu_dist_gesv(mplu_dist* d, int n, int nb, const double* const* dA, const l
     d->nb = nb;
     d->T = n / nb;
     d->gemm_launches = d->kernel_launches = 0;
+    d->trail_count = 0;
+    d->trail_flops = d->trail_bytes = 0;
     std::vector<const double*> bv, rv;
     std::vector<double*> xv;
     for (size_t i = 0; i < d->ranks.size(); ++i) {
@@ -861,6 +927,15 @@ int mplu_dist_gesv(mplu_dist* d, int n, int nb, const double* const* dA, const l
         stats->first_backward_error = first_be;
         stats->gemm_launches = d->gemm_launches;
         stats->kernel_launches = d->kernel_launches;
+        stats->trailing_launches = d->trail_count;
+        stats->trailing_flops = d->trail_flops;
+        stats->trailing_bytes = d->trail_bytes;
+        float tms = 0.f;
+        for (int t = 0; t < d->trail_count; ++t) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, d->trail_ev[2 * t], d->trail_ev[2 * t + 1]) == cudaSuccess) tms += ms;
+        }
+        stats->trailing_ms = tms;
         cudaEventElapsedTime(&stats->factor_ms, d->ev0, d->ev1);
         cudaEventElapsedTime(&stats->solve_ms, d->ev1, d->ev2);
         cudaEventElapsedTime(&stats->total_ms, d->ev0, d->ev2);
@@ -869,6 +944,73 @@ int mplu_dist_gesv(mplu_dist* d, int n, int nb, const double* const* dA, const l
     if (h_status & 1) return MPLU_E_OVERFLOW;
     if (h_status & 2) return MPLU_E_ZEROPIVOT;
     return MPLU_E_NOCONV;
+}
+
+// Same solve from HOST buffers (pinned or pageable): hA[i] = local block-cyclic fp64 tiles of logical rank i (host,
+// column-major, leading dimension lda[i]), hb[i] full right-hand side, hx[i] receives the full solution.  The H2D copies
+// of the local tiles and the D2H copy of x are inside the call; stats->h2d_ms / d2h_ms report them.
+int mplu_dist_gesv_host(mplu_dist* d, int n, int nb, const double* const* hA, const long long* lda,
+                        const double* const* hb, double* const* hx, const mplu_options* opts, mplu_stats* stats) {
+    if (!d || n <= 0 || nb < kDiagBlock || nb % kDiagBlock || n % nb || !hA || !lda || !hb || !hx) return MPLU_E_ARG;
+    CK(cudaSetDevice(d->device));
+    const size_t L = d->ranks.size();
+    if (d->stA.size() != L) { d->stA.assign(L, nullptr); d->stb.assign(L, nullptr); d->stx.assign(L, nullptr); d->stA_cap.assign(L, 0); d->st_n = 0; }
+    const int T = n / nb;
+    std::vector<long long> ld(L);
+    std::vector<const double*> pa(L), pb(L);
+    std::vector<double*> px(L);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, d->ranks[0].chain));
+    for (size_t i = 0; i < L; ++i) {
+        DRank& r = d->ranks[i];
+        const size_t ml = (size_t)tiles_local(T, d->P, r.p) * nb, nl = (size_t)tiles_local(T, d->Q, r.q) * nb;
+        const size_t need = (ml ? ml : 1) * (nl ? nl : 1);
+        if (need > d->stA_cap[i]) {
+            cudaFree(d->stA[i]); d->stA[i] = nullptr; d->stA_cap[i] = 0;
+            CK(cudaMalloc(&d->stA[i], need * sizeof(double)));
+            d->stA_cap[i] = need;
+        }
+        if (n > d->st_n || !d->stb[i]) {
+            cudaFree(d->stb[i]); cudaFree(d->stx[i]);
+            CK(cudaMalloc(&d->stb[i], n * sizeof(double)));
+            CK(cudaMalloc(&d->stx[i], n * sizeof(double)));
+        }
+        if (ml && nl) {
+            if (lda[i] < (long long)ml) return MPLU_E_ARG;
+            CK(cudaMemcpy2DAsync(d->stA[i], ml * sizeof(double), hA[i], (size_t)lda[i] * sizeof(double), ml * sizeof(double),
+                                 nl, cudaMemcpyHostToDevice, r.chain));
+        }
+        CK(cudaMemcpyAsync(d->stb[i], hb[i], n * sizeof(double), cudaMemcpyHostToDevice, r.chain));
+        ld[i] = (long long)(ml ? ml : 1);
+        pa[i] = d->stA[i]; pb[i] = d->stb[i]; px[i] = d->stx[i];
+    }
+    d->st_n = n > d->st_n ? n : d->st_n;
+    CK(cudaEventRecord(e1, d->ranks[0].chain));
+    int rc = mplu_dist_gesv(d, n, nb, pa.data(), ld.data(), pb.data(), px.data(), opts, stats);
+    if (rc != 0 && rc != MPLU_E_NOCONV) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    float h2d = 0.f, d2h = 0.f;
+    cudaEventElapsedTime(&h2d, e0, e1);
+    CK(cudaEventRecord(e0, d->ranks[0].chain));
+    for (size_t i = 0; i < L; ++i)
+        CK(cudaMemcpyAsync(hx[i], d->stx[i], n * sizeof(double), cudaMemcpyDeviceToHost, d->ranks[i].chain));
+    CK(cudaEventRecord(e1, d->ranks[0].chain));
+    for (size_t i = 0; i < L; ++i) CK(cudaStreamSynchronize(d->ranks[i].chain));
+    cudaEventElapsedTime(&d2h, e0, e1);
+    if (stats) { stats->h2d_ms = h2d; stats->d2h_ms = d2h; stats->total_ms += h2d + d2h; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+// Release the device staging buffers of mplu_dist_gesv_host.
+void mplu_dist_release_staging(mplu_dist* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (auto& p : d->stA) { cudaFree(p); p = nullptr; }
+    for (auto& p : d->stb) { cudaFree(p); p = nullptr; }
+    for (auto& p : d->stx) { cudaFree(p); p = nullptr; }
+    for (auto& c : d->stA_cap) c = 0;
+    d->st_n = 0;
 }
 
 // Copy logical rank i's local fp32 factors (L\U in block-cyclic local order, mloc x nloc) widened to fp64.
