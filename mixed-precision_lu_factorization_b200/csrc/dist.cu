@@ -469,7 +469,10 @@ int pick_side_sms(const mplu_dist* d, long long rows, long long cols, int max_si
 int enqueue_dist_factorization(mplu_dist* d) {
     const int nb = d->nb, T = d->T, P = d->P, Q = d->Q;
     const int bf16 = d->opts.precision == MPLU_BF16;
-    int side_sms = d->opts.side_sms > 0 ? d->opts.side_sms : 32;
+    // side_sms > 0: fixed chain-lane budget (default 32); side_sms < 0: adaptive per step up to |side_sms| (measured
+    // slower on power-capped boxes, where the trailing GEMM does not speed up with more SMs: 900 vs 874 ms at n=131072, N=2)
+    const bool adaptive = d->opts.side_sms < 0;
+    int side_sms = d->opts.side_sms > 0 ? d->opts.side_sms : (adaptive ? -d->opts.side_sms : 32);
     side_sms -= side_sms % 2;
     const bool two = d->opts.lookahead != 0 && side_sms >= 2 && side_sms <= d->num_sms - 16;
     auto chain_of = [](DRank& r) { return r.chain; };
@@ -507,7 +510,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
         for (size_t i = 0; i < d->ranks.size(); ++i) {
             DRank& r = d->ranks[i];
             const long long rows = r.mloc - (long long)cnt_le(k, P, r.p) * nb, cols = r.nloc - (long long)cnt_le(k, Q, r.q) * nb;
-            side[i] = (two && d->opts.side_sms >= 0) ? pick_side_sms(d, rows > 0 ? rows : 0, cols > 0 ? cols : 0, side_sms) : side_sms;
+            side[i] = (two && adaptive) ? pick_side_sms(d, rows > 0 ? rows : 0, cols > 0 ? cols : 0, side_sms) : side_sms;
         }
         // ---- chain lane: GETRF on the owner
         for (auto& r : d->ranks) {
@@ -549,7 +552,16 @@ int enqueue_dist_factorization(mplu_dist* d) {
         for (auto& r : d->ranks) {
             const int ilo = cnt_le(k, P, r.p), jlo = cnt_le(k, Q, r.q);
             const long long rows = r.mloc - (long long)ilo * nb, cols = r.nloc - (long long)jlo * nb;
-            const Lane ln{r.chain, two ? side[&r - &d->ranks[0]] : 0};
+            // SM budget of the panel GEMMs: the chain lane's share while the previous step's trailing update is the
+            // longer job, (almost) the whole GPU once the schedule is chain-bound and the bulk lane would idle anyway
+            int panel_sms = 0;
+            if (two) {
+                const int sd = side[&r - &d->ranks[0]];
+                const double upd_ms = 2.0 * (double)(rows + nb) * (double)(cols + nb) * nb / 1.0e15 * 1e3;
+                const double pan_ms = 2.0 * (double)nb * nb * ((r.q == qk ? rows : 0) + (r.p == pk ? cols : 0)) / (sd * 9.4e12 * 0.6) * 1e3;
+                panel_sms = (pan_ms + 1.5 > upd_ms) ? d->num_sms - 8 : sd;
+            }
+            const Lane ln{r.chain, panel_sms};
             if (k >= 2) CK(cudaStreamWaitEvent(r.chain, r.ev_panel[b], 0));  // update k-2 has consumed buffers b
             if (rows > 0) CKI(make_operand(&r.opLp[b], r.Lp[b], (uint64_t)rows, (uint64_t)nb, (uint64_t)rows));
             if (r.q == qk && rows > 0) {
