@@ -367,7 +367,8 @@ def main():
                     ms_per_step=ms_max, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=args.precision + " operands, f32 accumulate, f64 refinement", data="synthetic",
                     config=dict(workload=f"n={n} mixed-precision LU+IR on 1 B200 per rank (BASELINE.json configs[2])" if n == 32768
-                                else f"n={n} mixed-precision LU+IR", n=n, nb=int(opts.nb), rhs=1,
+                                else f"n={n} mixed-precision LU+IR", n=n,
+                                nb=int(opts.nb) or (2048 if n >= 12288 else (1024 if n >= 4096 else 512)), rhs=1,
                                 matrix="column-diagonally-dominant, values k/10 (reference generator distribution), seed=1+rank",
                                 l2_policy="inputs larger than L2 (A is %.1f GiB)" % (8.0 * n * n / 2 ** 30),
                                 parallelism=("replicas x%d" % world) if world > 1 else "single GPU"),

@@ -8,6 +8,7 @@ lib = m.load_library()
 f = lib.mplu_diag_lu128_timed
 f.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 4
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+evict = (sys.argv[2] != "warm") if len(sys.argv) > 2 else True
 torch.manual_seed(0)
 A = (torch.rand(128, 128, device="cuda") * 9.9 + torch.eye(128, device="cuda") * 700).t().contiguous().t()
 Li = torch.zeros(128, 128, device="cuda").t(); Ui = torch.zeros(128, 128, device="cuda").t()
@@ -15,7 +16,7 @@ junk = torch.empty(64 << 20, device="cuda")
 for _ in range(reps):
     W = A.clone()
     clk = torch.zeros(32, dtype=torch.int64, device="cuda")
-    junk.normal_()  # evict caches (incl. instruction lines) like the interleaved GEMMs do
+    if evict: junk.normal_()  # evict caches (incl. instruction lines) like the interleaved GEMMs do
     torch.cuda.synchronize()
     assert f(W.data_ptr(), W.stride(1), Li.data_ptr(), Ui.data_ptr(), clk.data_ptr(), None) == 0
     torch.cuda.synchronize()
