@@ -29,6 +29,16 @@ def flops(n):
     return 2.0 / 3.0 * float(n) ** 3
 
 
+def measured_traffic():
+    """DRAM bytes of one rank-2048 trailing-update launch from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic_gemm_trailing.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return dict(bytes_per_launch=d["dram_bytes_read"] + d["dram_bytes_write"], algorithmic_bytes=d["algorithmic_bytes"],
+                shape=d["shape"], tensor_pipe_active_pct=d["tensor_pipe_active_pct"], source=d["source"])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -247,7 +257,8 @@ def run_distributed(args, m, pk, rank, world, local):
                                   peak=pk["tc_sustained"], unit="TFLOP/s", frac=(ach / pk["tc_sustained"]) if ach else None,
                                   peak_kind=f"bf16_tflops_sustained ({pk['src']}); burst {pk['tc_burst']}", launches=tr_n,
                                   avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
-                                  share_of_step=(tr_ms / args.steps / ms_max) if ms_max > 0 else None, traffic=None),
+                                  share_of_step=(tr_ms / args.steps / ms_max) if ms_max > 0 else None,
+                                  traffic=(measured_traffic() or {}).get("bytes_per_launch"), traffic_detail=measured_traffic()),
                     headline_frac_of_peak=value / world / pk["tc_sustained"])
         print(json.dumps(line), flush=True)
     ds.close()
@@ -381,7 +392,7 @@ def main():
                                   launches=tr_n, avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
                                   share_of_step=(tr_ms / args.steps / ms) if ms > 0 else None,
                                   algorithmic_c_bytes_per_s=(tr_by / (tr_ms * 1e-3) / 1e9) if tr_ms > 0 else None,
-                                  traffic=None),
+                                  traffic=(measured_traffic() or {}).get("bytes_per_launch"), traffic_detail=measured_traffic()),
                     headline_frac_of_peak=value / world / pk["tc_sustained"])
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = dict(cpu_lapack_baseline(min(n, args.cpu_n)), kind="port")

@@ -77,5 +77,26 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_drivers(force: bool = False) -> None:
+    """drivers/benchmark and drivers/matrix_generator (C++ hosts of the reference's two CLI programs)."""
+    ddir = ROOT / "drivers"
+    gen, bench = ddir / "matrix_generator", ddir / "benchmark"
+    if force or not gen.exists() or gen.stat().st_mtime < (ddir / "matrix_generator.cpp").stat().st_mtime:
+        subprocess.run(["g++", "-O2", "-std=c++17", str(ddir / "matrix_generator.cpp"), "-o", str(gen)], check=True)
+    src = ddir / "benchmark.cpp"
+    if force or not bench.exists() or bench.stat().st_mtime < max(src.stat().st_mtime, LIB.stat().st_mtime):
+        defs = []
+        try:  # host LAPACK for the lapack_time column: scipy's OpenBLAS if present (loaded with dlopen at run time)
+            import glob
+            import scipy
+            libs = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+            if libs:
+                defs = [f'-DMPLU_DEFAULT_LAPACK_LIB="{libs[0]}"']
+        except Exception:
+            pass
+        subprocess.run(["g++", "-O2", "-std=c++17", *defs, "-I", str(ROOT / "include"), str(src), "-o", str(bench),
+                        f"-L{PKG}", "-lmplu", "-ldl", f"-Wl,-rpath,{PKG}"], check=True)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
