@@ -33,6 +33,7 @@ enum {
 
 enum { MPLU_FP16 = 0, MPLU_BF16 = 1 };
 enum { MPLU_GEMM_AUTO = -1, MPLU_GEMM_CG1 = 0, MPLU_GEMM_CG2 = 1 };
+enum { MPLU_REFINE_CLASSIC = 0, MPLU_REFINE_GMRES = 1 };
 
 typedef struct mplu_options {
     int precision;    /* MPLU_FP16 (default) or MPLU_BF16: panel/operand storage type; accumulation is fp32 */
@@ -48,6 +49,10 @@ typedef struct mplu_options {
     int use_graph;    /* 1 (default): capture the factorization schedule once per (n, options) into a CUDA graph */
     int pdl;          /* 1: programmatic dependent launches along each stream's kernel chain (default 0: measured slower, pre-launched CTAs take SMs from the other lane) */
     int group;        /* 1 (default): independent L-side / U-side products of a recursion node share one launch */
+    int refinement;   /* MPLU_REFINE_CLASSIC (default): d = (LU)^-1 r;  MPLU_REFINE_GMRES: GMRES on (LU)^-1 A d = (LU)^-1 r */
+    int gmres_restart;/* Krylov steps per correction at most (default 50) */
+    double gmres_tol; /* relative reduction of the preconditioned residual that ends a correction (default 1e-6) */
+    int bf16_fallback;/* 1 (default): an fp16 factorization whose scaled values left the fp16 range is redone in bf16 */
 } mplu_options;
 
 typedef struct mplu_stats {
@@ -71,6 +76,8 @@ typedef struct mplu_stats {
     float trailing_ms;      /* summed device time of those launches (CUDA events on the launching stream) */
     double trailing_flops;  /* their algorithmic flops, 2*M*N*K each */
     double trailing_bytes;  /* their algorithmic C traffic, 8*M*N bytes each (fp32 read + write) */
+    int gmres_iters;        /* MPLU_REFINE_GMRES: Krylov steps summed over the refinement iterations */
+    int precision_used;     /* MPLU_FP16 / MPLU_BF16: differs from the request after a bf16 fallback */
 } mplu_stats;
 
 void mplu_default_options(mplu_options *opts);

@@ -17,6 +17,7 @@ LIB_PATH = PKG_DIR / "libmplu.so"
 
 MPLU_FP16, MPLU_BF16 = 0, 1
 GEMM_AUTO, GEMM_CG1, GEMM_CG2 = -1, 0, 1
+REFINE_CLASSIC, REFINE_GMRES = 0, 1
 
 ERRORS = {
     0: "ok", -1: "bad argument", -2: "no CUDA device", -3: "not factored", -4: "TMA descriptor encoding failed",
@@ -27,7 +28,8 @@ ERRORS = {
 class Options(C.Structure):
     _fields_ = [("precision", C.c_int), ("nb", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double),
                 ("gemm_variant", C.c_int), ("max_sms", C.c_int), ("a_exp", C.c_int), ("l_exp", C.c_int),
-                ("lookahead", C.c_int), ("side_sms", C.c_int), ("use_graph", C.c_int), ("pdl", C.c_int), ("group", C.c_int)]
+                ("lookahead", C.c_int), ("side_sms", C.c_int), ("use_graph", C.c_int), ("pdl", C.c_int), ("group", C.c_int),
+                ("refinement", C.c_int), ("gmres_restart", C.c_int), ("gmres_tol", C.c_double), ("bf16_fallback", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -37,7 +39,7 @@ class Stats(C.Structure):
                 ("factor_ms", C.c_float), ("solve_ms", C.c_float), ("total_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("gemm_launches", C.c_int),
                 ("kernel_launches", C.c_int), ("trailing_launches", C.c_int), ("trailing_ms", C.c_float),
-                ("trailing_flops", C.c_double), ("trailing_bytes", C.c_double)]
+                ("trailing_flops", C.c_double), ("trailing_bytes", C.c_double), ("gmres_iters", C.c_int), ("precision_used", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

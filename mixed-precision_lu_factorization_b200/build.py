@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-I", str(ROOT / "include"),
 ]
 
-SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "dist.cu", "generate.cu", "mpf_compat.cu"]
+SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "gmres.cu", "dist.cu", "generate.cu", "mpf_compat.cu"]
 
 
 def _nvcc() -> str:

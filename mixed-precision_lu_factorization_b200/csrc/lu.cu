@@ -365,7 +365,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     CKI(launch_first_touch(dA, lda, n, c->W, npad, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
 
     const bool use_graph = c->opts.use_graph != 0;
-    mplu_context::GraphKey key{n, npad, c->opts.nb, c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
+    mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group, c->W};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
@@ -434,7 +434,7 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
 
     double h_norms[2] = {0, 0}, h_an[2] = {0, 0};
     const double eps = 2.220446049250313e-16 / 2.0;  // LAPACK dlamch('E')
-    int iters = 0, converged = 0;
+    int iters = 0, converged = 0, gmres_iters = 0;
     double first_be = -1.0;
     const int max_iters = c->opts.max_iters > 0 ? c->opts.max_iters : 30;
     for (;;) {
@@ -451,8 +451,14 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
         if (!(h_norms[0] == h_norms[0])) break;  // NaN: give up
         if (h_norms[0] <= thresh) { converged = 1; break; }
         if (iters >= max_iters) break;
-        CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, c->r, c->y, nullptr, dx, c->ready, st));
-        c->kernel_launches += solve_launches;
+        if (c->opts.refinement == MPLU_REFINE_GMRES) {
+            int inner = 0;
+            CKI(gmres_correction(c, dA, lda, dx, &inner));
+            gmres_iters += inner;
+        } else {
+            CKI(launch_lu_solve(c->W, ld, n, npad, c->Linv32, c->Uinv32, c->r, c->y, nullptr, dx, c->ready, st));
+            c->kernel_launches += solve_launches;
+        }
         ++iters;
     }
     int h_status = 0;
@@ -473,6 +479,7 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
         stats->trailing_launches = c->trail_count;
         stats->trailing_flops = c->trail_flops;
         stats->trailing_bytes = c->trail_bytes;
+        stats->gmres_iters = gmres_iters;
         float tms = 0.f;
         for (int i = 0; i < c->trail_count; ++i) {
             float ms = 0.f;
@@ -505,6 +512,10 @@ void mplu_default_options(mplu_options* o) {
     o->use_graph = 1;
     o->pdl = 0;
     o->group = 1;
+    o->refinement = MPLU_REFINE_CLASSIC;
+    o->gmres_restart = 50;
+    o->gmres_tol = 1e-6;
+    o->bf16_fallback = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -542,6 +553,7 @@ void mplu_destroy(mplu_context* c) {
     free_work(c);
     cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status); cudaFree(c->ready);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
+    cudaFree(c->gm_V); cudaFree(c->gm_w); cudaFree(c->gm_h); cudaFree(c->gm_zero);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_step) if (e) cudaEventDestroy(e);
@@ -586,6 +598,16 @@ int mplu_gesv_device(mplu_context* c, int n, const double* dA, long long lda, co
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[1], c->stream));
     rc = solve_impl(c, dA, lda, db, dx, stats);
+    if (rc == MPLU_E_OVERFLOW && c->opts.precision == MPLU_FP16 && c->opts.bf16_fallback) {
+        // like dsgesv's fall back to full precision: same algorithm, operand type without the range problem
+        c->opts.precision = MPLU_BF16;
+        c->factored = false;
+        rc = factor_impl(c, n, dA, lda);
+        if (rc) return rc;
+        if (stats) memset(stats, 0, sizeof(*stats));
+        rc = solve_impl(c, dA, lda, db, dx, stats);
+    }
+    if (stats) stats->precision_used = c->opts.precision;
     CK(cudaEventRecord(c->ev[2], c->stream));
     CK(cudaEventSynchronize(c->ev[2]));
     if (stats) {

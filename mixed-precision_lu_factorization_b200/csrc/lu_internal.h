@@ -36,6 +36,9 @@ struct mplu_context {
     double* norms = nullptr;  // [0] ||r||, [1] ||x||
     float* y = nullptr;       // 2*npad
     int nchunk = 64;
+    // GMRES-IR workspace (gmres.cu)
+    double* gm_V = nullptr; double* gm_w = nullptr; double* gm_h = nullptr; double* gm_zero = nullptr;
+    int gm_cap_n = 0, gm_cap_m = 0;
     // staging for the host variant
     double* dA_stage = nullptr; size_t dA_cap = 0;
     double* db_stage = nullptr; double* dx_stage = nullptr; size_t dv_cap = 0;
@@ -116,5 +119,7 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
 // c->Linv32 / c->Uinv32.  Everything is enqueued on `st`.
 int getrf_resident_tile(mplu_context* c, cudaStream_t st);
 int ensure_work(mplu_context* c, int n);
+// GMRES-IR: solve A d = c->r by GMRES preconditioned with the stored factors, x += d (gmres.cu)
+int gmres_correction(mplu_context* c, const double* dA, long long lda, double* dx, int* inner);
 
 }  // namespace mplu_detail

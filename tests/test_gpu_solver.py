@@ -143,3 +143,51 @@ def test_full_size_properties_n32768(mplu, solver):
     assert d["converged"] == 1 and d["status_bits"] == 0 and d["iters"] <= 3
     assert d["backward_error"] <= 1e-15 * n
     assert (x - 1).abs().max().item() <= 1e-11
+
+
+# ---- condition-number sweep (BASELINE.json configs[4]) and GMRES-based refinement -----------------------------------
+def _spd(oracle, n, kappa):
+    A = oracle.spd_kappa_matrix(n, kappa, seed=1)
+    return A, A.sum(axis=1)
+
+
+@pytest.mark.parametrize("kappa,prec,classic_ok", [(1e2, 0, True), (1e4, 0, True), (1e4, 1, True), (1e7, 0, False), (1e6, 1, False)])
+def test_kappa_sweep_classic_vs_gmres_refinement(mplu, oracle, solver, kappa, prec, classic_ok):
+    """SPD matrices with geometric spectrum.  Classic refinement with 16-bit factors converges while kappa * u16 is
+    small and stagnates beyond; GMRES-IR converges on all of them to the fp64 backward error a
+    host dgetrf/dgetrs solve (the reference's factors + a solve) reaches."""
+    n = 1024
+    A, b = _spd(oracle, n, kappa)
+    x_ref, _, _ = oracle.lapack_gesv(A, b)
+    r = b - A @ x_ref
+    be_ref = np.abs(r).max() / (np.abs(A).sum(axis=1).max() * np.abs(x_ref).max() + np.abs(b).max())
+    import torch
+    dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
+    db = torch.tensor(b, dtype=torch.float64, device="cuda")
+    x, st = solver.gesv(dA, db, mplu.default_options(precision=prec), allow_noconv=True)
+    assert bool(st.converged) == classic_ok, st.as_dict()
+    xg, sg = solver.gesv(dA, db, mplu.default_options(precision=prec, refinement=mplu.REFINE_GMRES), allow_noconv=True)
+    assert sg.converged == 1 and sg.gmres_iters >= sg.iters
+    assert sg.backward_error <= max(10 * be_ref, 2 * n * EPS)
+    if classic_ok:
+        assert sg.iters <= st.iters  # never more outer iterations than classic refinement
+    # forward error consistent with the conditioning
+    assert np.abs(xg.cpu().numpy() - 1).max() <= 100 * kappa * n * EPS
+
+
+def test_fp16_overflow_falls_back_to_bf16(mplu, oracle, solver):
+    """a matrix whose inverse factors leave the scaled fp16 range: reported (status bit 0) and redone in bf16"""
+    n = 512
+    A, b = _spd(oracle, n, 1e12)
+    import torch
+    dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
+    db = torch.tensor(b, dtype=torch.float64, device="cuda")
+    overflowed = False
+    try:
+        x, st = solver.gesv(dA, db, mplu.default_options(refinement=mplu.REFINE_GMRES, bf16_fallback=0), allow_noconv=True)
+    except mplu.MpluError as e:
+        assert e.code == -5  # MPLU_E_OVERFLOW: reported, not silent
+        overflowed = True
+    x2, st2 = solver.gesv(dA, db, mplu.default_options(refinement=mplu.REFINE_GMRES), allow_noconv=True)
+    assert st2.precision_used == (mplu.MPLU_BF16 if overflowed else mplu.MPLU_FP16)
+    assert np.isfinite(x2.cpu().numpy()).all()
