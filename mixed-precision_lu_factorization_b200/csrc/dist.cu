@@ -261,7 +261,7 @@ struct DRank {
     mplu_context* ctx = nullptr;   // options / status / small device words for the GEMM launches of this rank
     mplu_context* dctx = nullptr;  // nb x nb context that factors diagonal tiles
     cudaStream_t chain = nullptr, bulk = nullptr;
-    cudaEvent_t ev_tmp = nullptr, ev_chain = nullptr, ev_bulk = nullptr, ev_e1 = nullptr, ev_panel[2] = {nullptr, nullptr};
+    cudaEvent_t ev_tmp = nullptr, ev_chain = nullptr, ev_bulk = nullptr, ev_e1 = nullptr, ev_d = nullptr, ev_panel[2] = {nullptr, nullptr};
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
     int mt = 0, nt = 0;
     long long mloc = 0, nloc = 0;
@@ -514,8 +514,8 @@ int enqueue_dist_factorization(mplu_dist* d) {
         }
         // ---- chain lane: GETRF on the owner
         for (auto& r : d->ranks) {
-            if (k > 0) CK(cudaStreamWaitEvent(r.chain, r.ev_e1, 0));  // tile column / row k carry update k-1
             if (r.p != pk || r.q != qk) continue;
+            if (k > 0) CK(cudaStreamWaitEvent(r.chain, r.ev_d, 0));  // the diagonal tile carries update k-1
             const long long ik = k / P, jk = k / Q;
             mplu_context* dc = r.dctx;
             float* tile = r.W + ik * nb + jk * nb * r.mloc;
@@ -523,7 +523,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
                                  (size_t)nb * sizeof(float), nb, cudaMemcpyDeviceToDevice, r.chain));
             dc->gemm_launches = dc->kernel_launches = 0;
             dc->opts.max_sms = two ? side[&r - &d->ranks[0]] : 0;
-            CKI(getrf_resident_tile(dc, r.chain));
+            CKI(getrf_resident_tile(dc, r.chain, nb));
             d->gemm_launches += dc->gemm_launches;
             d->kernel_launches += dc->kernel_launches + 1;
             CK(cudaMemcpy2DAsync(tile, (size_t)r.mloc * sizeof(float), dc->W, (size_t)nb * sizeof(float),
@@ -552,6 +552,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
         for (auto& r : d->ranks) {
             const int ilo = cnt_le(k, P, r.p), jlo = cnt_le(k, Q, r.q);
             const long long rows = r.mloc - (long long)ilo * nb, cols = r.nloc - (long long)jlo * nb;
+            if (k > 0) CK(cudaStreamWaitEvent(r.chain, r.ev_e1, 0));  // tile column / row k carry update k-1
             // SM budget of the panel GEMMs: the chain lane's share while the previous step's trailing update is the
             // longer job, (almost) the whole GPU once the schedule is chain-bound and the bulk lane would idle anyway
             int panel_sms = 0;
@@ -604,6 +605,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
             CK(cudaEventRecord(r.ev_chain, r.chain));
             CK(cudaStreamWaitEvent(r.bulk, r.ev_chain, 0));
             if (rows <= 0 || cols <= 0) {
+                CK(cudaEventRecord(r.ev_d, r.bulk));
                 CK(cudaEventRecord(r.ev_e1, r.bulk));
                 CK(cudaEventRecord(r.ev_panel[b], r.bulk));
                 continue;
@@ -622,10 +624,16 @@ int enqueue_dist_factorization(mplu_dist* d) {
             };
             const long long R0 = (long long)ilo * nb, C0 = (long long)jlo * nb;
             long long c_rest = C0, r_rest = R0;
-            if (r.q == qn) {  // owns tile column k+1: first local tile column of the region
+            if (r.q == qn && r.p == pn) {  // owns the next diagonal tile: update it first, its GETRF heads the next step
+                CKI(update(R0, R0 + nb, C0, C0 + nb, true));
+                CK(cudaEventRecord(r.ev_d, r.bulk));
+                CKI(update(R0 + nb, r.mloc, C0, C0 + nb, true));
+                c_rest = C0 + nb;
+            } else if (r.q == qn) {  // owns tile column k+1: first local tile column of the region
                 CKI(update(R0, r.mloc, C0, C0 + nb, true));
                 c_rest = C0 + nb;
             }
+            if (!(r.q == qn && r.p == pn)) CK(cudaEventRecord(r.ev_d, r.bulk));
             if (r.p == pn) {  // owns tile row k+1
                 CKI(update(R0, R0 + nb, c_rest, r.nloc, true));
                 r_rest = R0 + nb;
@@ -759,7 +767,7 @@ static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
         CKI(mplu_create(&r.dctx, device));
         r.chain = r.ctx->stream;
         r.bulk = r.ctx->side;
-        cudaEvent_t* evs[] = {&r.ev_tmp, &r.ev_chain, &r.ev_bulk, &r.ev_e1, &r.ev_panel[0], &r.ev_panel[1]};
+        cudaEvent_t* evs[] = {&r.ev_tmp, &r.ev_chain, &r.ev_bulk, &r.ev_e1, &r.ev_d, &r.ev_panel[0], &r.ev_panel[1]};
         for (auto e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
     return 0;
@@ -816,7 +824,7 @@ void mplu_dist_destroy(mplu_dist* d) {
     cudaDeviceSynchronize();
     for (auto& r : d->ranks) {
         free_rank_work(r);
-        cudaEvent_t evs[] = {r.ev_tmp, r.ev_chain, r.ev_bulk, r.ev_e1, r.ev_panel[0], r.ev_panel[1]};
+        cudaEvent_t evs[] = {r.ev_tmp, r.ev_chain, r.ev_bulk, r.ev_e1, r.ev_d, r.ev_panel[0], r.ev_panel[1]};
         for (auto e : evs) if (e) cudaEventDestroy(e);
         mplu_destroy(r.ctx);
         mplu_destroy(r.dctx);

@@ -28,9 +28,9 @@ namespace mplu_detail {
 
 void free_work(mplu_context* c) {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    cudaFree(c->W); cudaFree(c->Wh); cudaFree(c->Fh); cudaFree(c->Linv16); cudaFree(c->Uinv16); cudaFree(c->Linv32);
-    cudaFree(c->Uinv32); cudaFree(c->Tb1); cudaFree(c->Tb2);
-    cudaFree(c->inv_scales); cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
+    cudaFree(c->slab);
+    cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
+    c->slab = nullptr; c->slab_bytes = 0;
     c->W = nullptr; c->Wh = c->Fh = nullptr; c->Linv16 = c->Uinv16 = c->Tb1 = c->Tb2 = nullptr;
     c->Linv32 = c->Uinv32 = nullptr; c->cap_nb = 0;
     c->inv_scales = nullptr; c->rowsum_part = nullptr; c->r = c->partial = nullptr; c->y = nullptr;
@@ -61,19 +61,28 @@ int ensure_work(mplu_context* c, int n) {
     if (npad > c->cap_npad || NB > c->cap_nb) {
         free_work(c);
         const size_t np = (size_t)npad, nb = (size_t)NB;
-        CK(cudaMalloc(&c->W, np * np * sizeof(float)));
-        CK(cudaMalloc(&c->Wh, np * np * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Fh, np * np * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Linv16, np * nb * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Uinv16, np * nb * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Tb1, nb * nb * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Tb2, nb * nb * sizeof(uint16_t)));
-        CK(cudaMalloc(&c->Linv32, np * kDiagBlock * sizeof(float)));
-        CK(cudaMalloc(&c->Uinv32, np * kDiagBlock * sizeof(float)));
+        // every array the GEMMs and diag_lu touch lives in ONE allocation, so that a diagonal tile's whole working set
+        // can be named by a single L2 access-policy window (see tile workspace below)
+        auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
+        const size_t szW = up(np * np * sizeof(float)), sz16 = up(np * np * sizeof(uint16_t)), szI = up(np * nb * sizeof(uint16_t)),
+                     szT = up(nb * nb * sizeof(uint16_t)), sz32 = up(np * kDiagBlock * sizeof(float)),
+                     szS = up(4 * (np / kDiagBlock) * sizeof(float));
+        c->slab_bytes = szW + 2 * sz16 + 2 * szI + 2 * szT + 2 * sz32 + szS;
+        CK(cudaMalloc(&c->slab, c->slab_bytes));
+        char* q = reinterpret_cast<char*>(c->slab);
+        c->W = reinterpret_cast<float*>(q); q += szW;
+        c->Wh = reinterpret_cast<uint16_t*>(q); q += sz16;
+        c->Fh = reinterpret_cast<uint16_t*>(q); q += sz16;
+        c->Linv16 = reinterpret_cast<uint16_t*>(q); q += szI;
+        c->Uinv16 = reinterpret_cast<uint16_t*>(q); q += szI;
+        c->Tb1 = reinterpret_cast<uint16_t*>(q); q += szT;
+        c->Tb2 = reinterpret_cast<uint16_t*>(q); q += szT;
+        c->Linv32 = reinterpret_cast<float*>(q); q += sz32;
+        c->Uinv32 = reinterpret_cast<float*>(q); q += sz32;
+        c->inv_scales = reinterpret_cast<float*>(q);
         // diag_lu only stores the triangles of the fp32 inverses: the other halves stay zero from here on
         CK(cudaMemset(c->Linv32, 0, np * kDiagBlock * sizeof(float)));
         CK(cudaMemset(c->Uinv32, 0, np * kDiagBlock * sizeof(float)));
-        CK(cudaMalloc(&c->inv_scales, 4 * (np / kDiagBlock) * sizeof(float)));
         CK(cudaMalloc(&c->rowsum_part, (size_t)c->nchunk * np * sizeof(double)));
         CK(cudaMalloc(&c->r, np * sizeof(double)));
         CK(cudaMalloc(&c->partial, (size_t)c->nchunk * np * sizeof(double)));
@@ -224,16 +233,77 @@ struct Sched {
     }
 };
 
-int getrf_resident_tile(mplu_context* c, cudaStream_t st) {
-    const int nb = c->npad;
-    const long long ld = nb;
+int getrf_resident_tile(mplu_context* c, cudaStream_t st, int w) {
+    const long long ld = c->npad;  // the workspace's leading dimension (its allocation), w <= npad is the tile width
     const int bf16 = c->opts.precision == MPLU_BF16;
     const Lane ln{st, c->opts.max_sms};
-    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, nb, nb, c->scales + SC_A, bf16, c->status, st));
-    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * nb * sizeof(uint16_t), st));
-    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * nb * sizeof(uint16_t), st));
+    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, w, w, c->scales + SC_A, bf16, c->status, st));
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * w * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * w * sizeof(uint16_t), st));
     const Sched S{c, ld, (long long)c->cap_nb};
-    return S.getrf(ln, 0, 0, nb);
+    return S.getrf(ln, 0, 0, w);
+}
+
+// GETRF of the diagonal tile [T, T+w)^2 of context c in the compact workspace context c->tile (its arrays are one slab
+// that the chain lane keeps resident in L2 with an access-policy window while the bulk lane streams the trailing matrix
+// through the cache): copy the tile in, factor it there, copy L\U, the 16-bit inverses (into the bands), the fp32 block
+// inverses and the tile's scales back.
+int getrf_in_workspace(mplu_context* c, const Lane& ln, int T, int w) {
+    mplu_context* t = c->tile;
+    const long long ld = c->npad, tld = t->npad;
+    cudaStream_t st = ln.st;
+    const size_t wb = (size_t)w;
+    t->opts.max_sms = lane_sms(c, ln);
+    t->opts.precision = c->opts.precision;
+    int* own_status = t->status;
+    t->status = c->status;  // the tile's kernels report into the caller's status word
+    CK(cudaMemcpy2DAsync(t->W, (size_t)tld * sizeof(float), c->W + T + (long long)T * ld, (size_t)ld * sizeof(float),
+                         wb * sizeof(float), wb, cudaMemcpyDeviceToDevice, st));
+    t->gemm_launches = t->kernel_launches = 0;
+    int rc = getrf_resident_tile(t, st, w);
+    t->status = own_status;
+    if (rc) return rc;
+    c->gemm_launches += t->gemm_launches;
+    c->kernel_launches += t->kernel_launches + 1;
+    CK(cudaMemcpy2DAsync(c->W + T + (long long)T * ld, (size_t)ld * sizeof(float), t->W, (size_t)tld * sizeof(float),
+                         wb * sizeof(float), wb, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(c->Linv16 + (long long)T * c->cap_nb, (size_t)c->cap_nb * 2, t->Linv16, (size_t)t->cap_nb * 2, wb * 2, wb,
+                         cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(c->Uinv16 + (long long)T * c->cap_nb, (size_t)c->cap_nb * 2, t->Uinv16, (size_t)t->cap_nb * 2, wb * 2, wb,
+                         cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->Linv32 + (size_t)T * kDiagBlock, t->Linv32, wb * kDiagBlock * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->Uinv32 + (size_t)T * kDiagBlock, t->Uinv32, wb * kDiagBlock * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->inv_scales + 4 * (T / kDiagBlock), t->inv_scales, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// Create / size the tile workspace and pin it in L2 for the stream the diagonal tiles are factored on.
+int prepare_tile_workspace(mplu_context* c, int NB, cudaStream_t getrf_stream) {
+    if (!c->tile) CKI(mplu_create(&c->tile, c->device));
+    mplu_context* t = c->tile;
+    t->opts = c->opts;
+    t->opts.nb = NB;
+    t->opts.lookahead = 0;
+    t->opts.use_graph = 0;
+    CKI(ensure_work(t, NB));
+    if (c->opts.l2_persist) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        size_t want = t->slab_bytes;
+        if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t carve = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = t->slab;
+            attr.accessPolicyWindow.num_bytes = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
+            attr.accessPolicyWindow.hitRatio = (float)((double)carve / (double)attr.accessPolicyWindow.num_bytes);
+            if (attr.accessPolicyWindow.hitRatio > 1.f) attr.accessPolicyWindow.hitRatio = 1.f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(getrf_stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
+    }
+    return 0;
 }
 
 int record_event(mplu_context* c, cudaEvent_t ev, cudaStream_t st) {
@@ -286,7 +356,9 @@ int enqueue_factorization(mplu_context* c) {
     CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
     CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
 
-    CKI(S.getrf(all, 0, 0, NB));
+    const bool ws = c->opts.tile_ws != 0 && npad > NB;
+    if (ws) CK(cudaMemcpyAsync(c->tile->scales, c->scales, SC_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (ws) CKI(getrf_in_workspace(c, all, 0, NB)); else CKI(S.getrf(all, 0, 0, NB));
     if (two) {
         CK(cudaEventRecord(c->ev_fork, st));
         CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
@@ -310,7 +382,7 @@ int enqueue_factorization(mplu_context* c) {
         }
         CKI(S.schur(chain, k1, k2, k1, k2, k0, k1, nbn, nbn));
         CKI(mark(c, 2000 + step, chain.st));
-        CKI(S.getrf(chain, k1, k1, nbn));
+        if (ws) CKI(getrf_in_workspace(c, chain, k1, nbn)); else CKI(S.getrf(chain, k1, k1, nbn));
         CKI(mark(c, 3000 + step, chain.st));
         if (two) { CKI(step_event(c, step + 1, EV_GETRF, &ev)); CK(cudaEventRecord(ev, chain.st)); }
         // ---- bulk lane: the other rows/columns of the panels, then the trailing update
@@ -365,8 +437,16 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     CKI(launch_first_touch(dA, lda, n, c->W, npad, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
 
     const bool use_graph = c->opts.use_graph != 0;
+    {
+        const int NB = effective_nb(c, npad);
+        if (c->opts.tile_ws != 0 && npad > NB) {
+            const bool two = c->opts.lookahead != 0 && npad > 2 * NB;
+            CKI(prepare_tile_workspace(c, NB, two ? c->side : st));
+        }
+    }
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
-                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group, c->W};
+                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group, c->opts.tile_ws,
+                               c->W, c->tile ? (const void*)c->tile->W : nullptr};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
         c->gemm_launches = 0;
@@ -516,6 +596,8 @@ void mplu_default_options(mplu_options* o) {
     o->gmres_restart = 50;
     o->gmres_tol = 1e-6;
     o->bf16_fallback = 1;
+    o->tile_ws = 0;
+    o->l2_persist = 0;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -554,6 +636,7 @@ void mplu_destroy(mplu_context* c) {
     cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status); cudaFree(c->ready);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
     cudaFree(c->gm_V); cudaFree(c->gm_w); cudaFree(c->gm_h); cudaFree(c->gm_zero);
+    if (c->tile) { mplu_destroy(c->tile); c->tile = nullptr; }
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_step) if (e) cudaEventDestroy(e);

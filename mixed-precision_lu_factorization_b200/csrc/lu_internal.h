@@ -21,6 +21,9 @@ struct mplu_context {
     uint16_t* Tb1 = nullptr;     // nbcap x nbcap scratch of the inverse merges (L side, U side)
     uint16_t* Tb2 = nullptr;
     int cap_nb = 0;
+    void* slab = nullptr;        // the single allocation behind W .. inv_scales
+    size_t slab_bytes = 0;
+    mplu_context* tile = nullptr;  // nb x nb workspace context in which diagonal tiles are factored (L2-resident)
     float* Linv32 = nullptr;
     float* Uinv32 = nullptr;
     float* inv_scales = nullptr;  // 4 per diagonal block
@@ -55,7 +58,7 @@ struct mplu_context {
     static constexpr int kMaxSteps = 512;
     cudaEvent_t ev_step[4 * kMaxSteps] = {};  // per step: GETRF done, next-tile TRSM done, b2 done, b3a done
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group; const void* W; } gkey{};
+    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group, tile_ws; const void* W; const void* TW; } gkey{};
     int g_gemm_launches = 0, g_kernel_launches = 0, g_trail_count = 0;
     double g_trail_flops = 0, g_trail_bytes = 0;
     bool capturing = false;
@@ -117,7 +120,7 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
 // c->scales, factors the tile recursively and leaves L\U in c->W, the merged 16-bit inverses in c->Linv16 /
 // c->Uinv16 (nb x nb, ld = c->cap_nb), their scales in c->inv_scales[0..3] and the fp32 128-block inverses in
 // c->Linv32 / c->Uinv32.  Everything is enqueued on `st`.
-int getrf_resident_tile(mplu_context* c, cudaStream_t st);
+int getrf_resident_tile(mplu_context* c, cudaStream_t st, int w);
 int ensure_work(mplu_context* c, int n);
 // GMRES-IR: solve A d = c->r by GMRES preconditioned with the stored factors, x += d (gmres.cu)
 int gmres_correction(mplu_context* c, const double* dA, long long lda, double* dx, int* inner);
