@@ -1,6 +1,6 @@
 // matrix_generator -- writes the text input of the benchmark driver.
 // Same command line and file format as the reference generator (/root/reference/matrix_generator.cpp:8-11,53-85):
-//     matrix_generator filename maxSize [step=2] [function=exp (exp/lin)] [sparsity=0.0] [kind=rand (rand/dd)]
+//     matrix_generator filename maxSize [step=2] [function=exp (exp/lin)] [sparsity=0.0] [kind=rand (rand/dd/spd:KAPPA[:SEED])]
 // first line = number of matrices (written last, over a 16-character placeholder), then per matrix its size n and
 // n rows of n values.  With kind=rand the libc rand() stream is consumed exactly like the reference does (one draw
 // per element when sparsity == 0, an extra draw per element otherwise; never seeded), so the files are byte-identical.
@@ -8,8 +8,14 @@
 // factors -- it reads the values sequentially as column-major storage (benchmark.cpp:192-194), i.e. the transpose of
 // what is printed -- is strictly column diagonally dominant: partial pivoting then never swaps and the mixed-
 // precision no-pivot solver applies.
+// kind=spd:KAPPA[:SEED] (new) writes symmetric positive definite matrices H diag(sigma) H with one Householder
+// reflector H = I - 2uu^T and singular values geometric in [1/KAPPA, 1] (BASELINE.json's condition-number sweep); it
+// uses its own seeded generator and prints 17 significant digits; libc rand() is not touched.
+#include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -55,11 +61,21 @@ int main(int argc, char** argv) {
         }
     }
     bool dominant = false;
+    double kappa = 0.0;  // > 0: SPD mode
+    uint64_t seed = 1;
     if (argc > 6) {
         const std::string k = argv[6];
         if (k == "dd") dominant = true;
-        else if (k != "rand") {
-            std::cout << "Invalid kind: " << k << ". Use 'rand' or 'dd'." << std::endl;
+        else if (k.rfind("spd:", 0) == 0) {
+            char* end = nullptr;
+            kappa = std::strtod(k.c_str() + 4, &end);
+            if (end && *end == ':') seed = std::strtoull(end + 1, nullptr, 10);
+            if (!(kappa >= 1.0)) {
+                std::cout << "Invalid kind: " << k << ". spd needs KAPPA >= 1." << std::endl;
+                return -1;
+            }
+        } else if (k != "rand") {
+            std::cout << "Invalid kind: " << k << ". Use 'rand', 'dd' or 'spd:KAPPA[:SEED]'." << std::endl;
             return -1;
         }
     }
@@ -70,6 +86,41 @@ int main(int argc, char** argv) {
     for (int n = 2; n <= max_size; n = geometric ? n * step : n + step) {
         out << n << std::endl;
         row.resize(n);
+        if (kappa > 0.0) {
+            // A = D - 2 u (Du)^T - 2 (Du) u^T + 4 (u^T D u) u u^T,  D = diag(sigma),  O(n^2)
+            std::vector<double> u(n), du(n), sig(n);
+            uint64_t x = seed * 0x9E3779B97F4A7C15ull + (uint64_t)n;
+            double nrm = 0.0;
+            for (int i = 0; i < n; ++i) {  // splitmix64 -> uniform (-1, 1)
+                x += 0x9E3779B97F4A7C15ull;
+                uint64_t z = x;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                u[i] = (double)(z >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+                nrm += u[i] * u[i];
+            }
+            nrm = std::sqrt(nrm);
+            double udu = 0.0;
+            for (int i = 0; i < n; ++i) {
+                u[i] /= nrm;
+                sig[i] = std::pow(kappa, -(double)i / (double)(n > 1 ? n - 1 : 1));
+                du[i] = sig[i] * u[i];
+                udu += u[i] * du[i];
+            }
+            out << std::setprecision(17);
+            for (int i = 0; i < n; ++i) {
+                for (int j = 0; j < n; ++j) {
+                    double v = -2.0 * u[i] * du[j] - 2.0 * du[i] * u[j] + 4.0 * udu * u[i] * u[j];
+                    if (i == j) v += sig[i];
+                    out << v << " ";
+                }
+                out << std::endl;
+            }
+            out << std::setprecision(6) << std::endl;
+            ++count;
+            continue;
+        }
         for (int i = 0; i < n; ++i) {
             double off = 0.0;
             for (int j = 0; j < n; ++j) {

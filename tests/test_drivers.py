@@ -54,6 +54,16 @@ def test_generator_dd_mode_is_column_dominant_as_read_by_the_driver(mplu, tmp_pa
         assert np.array_equal(A[mask], R[mask])           # same rand() draws off the diagonal
 
 
+def test_generator_spd_kappa_mode(mplu, tmp_path):
+    f = tmp_path / "spd.txt"
+    subprocess.run([GEN, str(f), "32", "2", "exp", "0.0", "spd:1e4:7"], check=True, capture_output=True)
+    for A in read_matrices(f):
+        n = A.shape[0]
+        assert np.abs(A - A.T).max() <= 1e-15
+        w = np.linalg.eigvalsh(A)
+        assert w.min() > 0 and abs(w.max() - 1.0) < 1e-12 and abs(w.max() / w.min() / 1e4 - 1.0) < 1e-6
+
+
 def test_generator_usage_and_argument_errors(mplu, tmp_path):
     assert subprocess.run([GEN], capture_output=True).returncode != 0
     for bad in (["0"], ["8", "0"], ["8", "2", "cubic"], ["8", "2", "exp", "1.5"], ["8", "2", "exp", "0.0", "spd"]):
