@@ -55,6 +55,7 @@ typedef struct mplu_options {
     int bf16_fallback;/* 1 (default): an fp16 factorization whose scaled values left the fp16 range is redone in bf16 */
     int tile_ws;      /* 1: diagonal tiles are factored in a compact nb x nb workspace, copied in / out (default 0: measured
                          neutral, 43.3 vs 43.0 ms at n=32768) */
+    int cg2_min_elems;/* MPLU_GEMM_AUTO: products with M*N below this use single-CTA tiles even when M > 128 */
     int l2_persist;   /* 1: with tile_ws, pin that workspace in L2 through an access-policy window on the chain lane's
                          stream (default 0: measured much slower, 62.6 ms -- the carve-out starves the trailing GEMM) */
 } mplu_options;

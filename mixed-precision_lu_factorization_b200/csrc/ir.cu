@@ -93,6 +93,10 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
 // Steps complete strictly in order; `ready` = number of completed steps is published with a release store and polled
 // with acquire loads.  CTA c owns steps c, c+G, ... in ascending order and the launch is cooperative (all CTAs are
 // co-resident), so every wait is on a step owned by a running CTA.  HBM-bound: 4*n^2 bytes per solve.
+// Hand-off of a solved block: the solution vectors are pre-filled with NaN and consumers poll the DATA itself (the 16
+// floats a thread needs) instead of the counter: one L2 round trip less on the 2*n/128-step dependency chain and no
+// fence + flag store before the next step can start.  The counter is still published and is consulted every 64
+// polls, so a genuine NaN in the solution (broken factorization) cannot hang the sweep.
 constexpr int TSV_THREADS = 256;
 constexpr int DBS = kDiagBlock;
 constexpr int TSV_SMEM_BYTES = DBS * DBS * (int)sizeof(float);
@@ -104,6 +108,19 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_relaxed_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_f1(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f1(float* p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
@@ -144,13 +161,18 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)q * ldw));
             const unsigned need = (back ? nblk : 0) + tt + 1;
-            while (seen < need) seen = ld_acquire_u32(ready);
             const float4* sp = reinterpret_cast<const float4*>(solv + j * DBS + 16 * cg);
             float sv[16];
+            for (int spin = 0;; ++spin) {
+                bool pending = false;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 x4 = __ldcg(sp + q);
-                sv[4 * q] = x4.x; sv[4 * q + 1] = x4.y; sv[4 * q + 2] = x4.z; sv[4 * q + 3] = x4.w;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x4 = ld_relaxed_f4(sp + q);
+                    sv[4 * q] = x4.x; sv[4 * q + 1] = x4.y; sv[4 * q + 2] = x4.z; sv[4 * q + 3] = x4.w;
+                    pending |= (x4.x != x4.x) | (x4.y != x4.y) | (x4.z != x4.z) | (x4.w != x4.w);
+                }
+                if (!pending || seen >= need) break;
+                if ((spin & 63) == 63) seen = ld_acquire_u32(ready);  // a NaN that is data, not "not yet written"
             }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -161,14 +183,18 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             }
         }
         *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = acc;
-        if (back) while (seen < (unsigned)nblk) seen = ld_acquire_u32(ready);  // y of this block row must be final
         cp_async_wait_all();
         __syncthreads();
         if (tid < DBS) {
             const int row = i * DBS + tid;
             float a;
-            if (back) a = __ldcg(ysol + row);
-            else a = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
+            if (back) {  // y of this block row must be final (written by the forward sweep of this launch, or given)
+                for (int spin = 0;; ++spin) {
+                    a = ld_relaxed_f1(ysol + row);
+                    if (a == a || seen >= (unsigned)nblk) break;
+                    if ((spin & 63) == 63) seen = ld_acquire_u32(ready);
+                }
+            } else a = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
 #pragma unroll
             for (int g = 0; g < 8; ++g) a -= s_part[g][tid];
             s_acc[tid] = a;
@@ -190,13 +216,13 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             const float v = s_part[0][tid] + s_part[1][tid];
             const int row = i * DBS + tid;
             if (back) {
-                xsol[row] = v;
+                st_relaxed_f1(xsol + row, v);
                 if (row < n) {
                     if (d_out) d_out[row] = static_cast<double>(v);
                     if (x_accum) x_accum[row] += static_cast<double>(v);
                 }
             } else {
-                ysol[row] = v;
+                st_relaxed_f1(ysol + row, v);
             }
         }
         __syncthreads();
@@ -246,6 +272,9 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
     int nblk = npad / DBS;
     int s_begin = mode == 2 ? nblk : 0, s_end = mode == 1 ? nblk : 2 * nblk;
     set_u32_kernel<<<1, 1, 0, st>>>(ready, (unsigned)s_begin);
+    // NaN-fill what this launch produces: consumers poll the data (mode 2 takes its right-hand side in ysol)
+    if (mode != 2) cudaMemsetAsync(ysol, 0xFF, (size_t)npad * sizeof(float), st);
+    if (mode != 1 && xsol) cudaMemsetAsync(xsol, 0xFF, (size_t)npad * sizeof(float), st);
     const int grid = nblk < max_grid ? nblk : max_grid;
     void* args[] = {(void*)&W, (void*)&ldw, (void*)&n, (void*)&nblk, (void*)&Linv32, (void*)&Uinv32, (void*)&rhs,
                     (void*)&ysol, (void*)&xsol, (void*)&d_out, (void*)&x_accum, (void*)&ready, (void*)&s_begin,

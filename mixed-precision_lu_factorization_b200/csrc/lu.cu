@@ -123,7 +123,11 @@ GemmParams gemm_params(const mplu_context* c, const GemmCall& g) {
 
 int pick_variant(const mplu_context* c, const GemmCall& g) {
     if (c->opts.gemm_variant == MPLU_GEMM_CG1) return GEMM_CG1_AMN;
-    return (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
+    if (c->opts.gemm_variant == MPLU_GEMM_CG2) return (g.M > 128) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
+    // AUTO: CTA pairs (256x256 tiles) pay off once there is enough work to amortise the cluster set-up; the small
+    // products inside a diagonal tile's GETRF run as single-CTA 128x256 tiles
+    const long long cg2_min = c->opts.cg2_min_elems > 0 ? c->opts.cg2_min_elems : (1ll << 62);
+    return (g.M > 128 && (long long)g.M * g.N >= cg2_min) ? GEMM_CG2_AMN : GEMM_CG1_AMN;
 }
 
 int lane_sms(const mplu_context* c, const Lane& ln) {
@@ -445,7 +449,8 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
         }
     }
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
-                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group, c->opts.tile_ws,
+                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
+                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8),
                                c->W, c->tile ? (const void*)c->tile->W : nullptr};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
@@ -598,6 +603,7 @@ void mplu_default_options(mplu_options* o) {
     o->bf16_fallback = 1;
     o->tile_ws = 0;
     o->l2_persist = 0;
+    o->cg2_min_elems = 2048 * 2048;
 }
 
 int mplu_create(mplu_context** out, int device) {
