@@ -3,6 +3,9 @@
 // structure: r = b - A*x in fp64, L U d = r in the factorization precision, x += d in fp64.
 // All of them are HBM-bound: the residual streams 8*n^2 bytes, the solve pair 4*n^2 bytes.
 #include "kernels.h"
+#include "ptx.cuh"
+
+#include <cstdlib>
 
 namespace mplu {
 
@@ -97,9 +100,16 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
 // floats a thread needs) instead of the counter: one L2 round trip less on the 2*n/128-step dependency chain and no
 // fence + flag store before the next step can start.  The counter is still published and is consulted every 64
 // polls, so a genuine NaN in the solution (broken factorization) cannot hang the sweep.
+// Step s -> step s+1 is the critical chain (2*n/128 links); consecutive steps belong to consecutive CTAs, which are
+// launched as thread-block clusters of 8: the solver of step s also stores its block straight into mailboxes in the
+// shared memory of the CTAs that own steps s+1 .. s+3 (DSMEM), which poll their own shared memory for their three
+// newest operands instead of L2 (with only the newest one delivered, the second newest -- still in flight through L2
+// when the newest arrives -- kept the chain at L2 latency).  Hand-offs across a cluster boundary and all older
+// operands (which have slack) go through L2.
 constexpr int TSV_THREADS = 256;
 constexpr int DBS = kDiagBlock;
 constexpr int TSV_SMEM_BYTES = DBS * DBS * (int)sizeof(float);
+constexpr int TSV_MB = 3;  // mailbox depth: blocks of the TSV_MB preceding steps arrive through DSMEM
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -132,17 +142,30 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __global__ void __launch_bounds__(TSV_THREADS)
 lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
                 const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
-                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end) {
+                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end,
+                int use_mbox) {
     extern __shared__ __align__(16) float s_inv[];  // 128 x 128 inverse of the step's diagonal block
     __shared__ __align__(16) float s_part[8][DBS];
     __shared__ float s_acc[DBS];
+    __shared__ __align__(16) float mbox[2][TSV_MB][DBS];  // [owned-step parity][distance-1]: blocks of steps s-1 .. s-TSV_MB
     const int tid = threadIdx.x;
     const int rg = tid & 31, cg = tid >> 5;  // rows 4rg.., columns 16cg.. of a tile
     unsigned seen = 0;
+    unsigned crank = 0, csize = 1;
+    if (use_mbox) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+        for (int e = tid; e < 2 * TSV_MB * DBS; e += TSV_THREADS) (&mbox[0][0][0])[e] = __int_as_float(0x7fffffff);
+        ptx::cluster_sync_all();  // nobody stores into a mailbox that is not initialised yet
+    }
+    int kown = 0;
     // steps [s_begin, s_end): [0, 2*nblk) = both sweeps; [0, nblk) forward only; [nblk, 2*nblk) backward only (its
     // right-hand side is then read from ysol and *ready must start at nblk)
-    for (int s = s_begin + blockIdx.x; s < s_end; s += gridDim.x) {
+    for (int s = s_begin + blockIdx.x; s < s_end; s += gridDim.x, ++kown) {
         const bool back = s >= nblk;
+        // step s-d (d <= TSV_MB) was solved by CTA crank-d of this cluster: its block arrives in mbox[kown & 1][d-1]
+        auto delivered = [&](int d) { return use_mbox && (int)crank >= d && s - d >= s_begin; };
+        volatile float (*mb)[DBS] = mbox[kown & 1];
         const int t = back ? s - nblk : s;         // tiles in this block row
         const int i = back ? nblk - 1 - t : t;     // block row
         const float* solv = back ? xsol : ysol;
@@ -152,18 +175,42 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             for (int u = 0; u < DBS * DBS / 4 / TSV_THREADS; ++u)
                 cp_async16(s_inv + 4 * (tid + u * TSV_THREADS), inv + 4 * (tid + u * TSV_THREADS));
         }
+        // this row block's right-hand side: fetched NOW, long before the step's turn (loading it after the last operand
+        // arrived put one L2/HBM latency on every link of the dependency chain)
+        float a_pre = __int_as_float(0x7fffffff);
+        if (tid < DBS) {
+            const int row = i * DBS + tid;
+            if (back) a_pre = ld_relaxed_f1(ysol + row);  // may still be NaN = not solved yet: polled again below
+            else a_pre = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* wrow = W + (long long)i * DBS + 4 * rg;
-        for (int tt = 0; tt < t; ++tt) {
+        // 128-bit loads of this thread's 4 rows x 16 columns of tile tt
+        auto load_tile = [&](float4 (&v)[16], int tt) {
             const int j = back ? nblk - 1 - tt : tt;
             const float* wp = wrow + ((long long)j * DBS + 16 * cg) * ldw;
-            float4 v[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)q * ldw));
+        };
+        // wait for the solution block tile tt multiplies (mailbox for the newest ones, else L2), then accumulate
+        auto consume = [&](const float4 (&v)[16], int tt) {
+            const int j = back ? nblk - 1 - tt : tt;
             const unsigned need = (back ? nblk : 0) + tt + 1;
             const float4* sp = reinterpret_cast<const float4*>(solv + j * DBS + 16 * cg);
             float sv[16];
-            for (int spin = 0;; ++spin) {
+            bool got = false;
+            if (t - tt <= TSV_MB && delivered(t - tt)) {  // one of the newest operands: poll the local mailbox
+                volatile float* m = mb[t - tt - 1];
+                for (int spin = 0; spin < (1 << 20) && !got; ++spin) {
+                    got = true;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        sv[q] = m[16 * cg + q];
+                        got &= (sv[q] == sv[q]);
+                    }
+                }
+            }
+            for (int spin = 0; !got; ++spin) {
                 bool pending = false;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -181,20 +228,46 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
                 acc.z = fmaf(v[q].z, sv[q], acc.z);
                 acc.w = fmaf(v[q].w, sv[q], acc.w);
             }
+        };
+        // Two register buffers: the loads of tile tt+1 are in flight while the thread waits for the operand of tile tt.
+        // (With a single buffer a CTA that had caught up with the sweep's frontier paid one HBM latency per tile on
+        // top of the operand latency and set the pace of the whole dependency chain: 2.4 us per step.)
+        {
+            float4 va[16], vb[16];
+            if (t > 0) load_tile(va, 0);
+            for (int tt = 0; tt < t; tt += 2) {
+                if (tt + 1 < t) load_tile(vb, tt + 1);
+                consume(va, tt);
+                if (tt + 1 < t) {
+                    if (tt + 2 < t) load_tile(va, tt + 2);
+                    consume(vb, tt + 1);
+                }
+            }
         }
         *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = acc;
         cp_async_wait_all();
         __syncthreads();
         if (tid < DBS) {
             const int row = i * DBS + tid;
-            float a;
-            if (back) {  // y of this block row must be final (written by the forward sweep of this launch, or given)
-                for (int spin = 0;; ++spin) {
+            float a = a_pre;
+            if (back && a != a) {  // y of this block row must be final (written by the forward sweep of this launch, or given)
+                // y of block row i was solved at forward step i = s - (2t+1): near the turn it sits in a mailbox
+                if (2 * t + 1 <= TSV_MB && delivered(2 * t + 1))
+                    for (int spin = 0; spin < (1 << 20) && a != a; ++spin) a = mb[2 * t][tid];
+                for (int spin = 0; a != a; ++spin) {
                     a = ld_relaxed_f1(ysol + row);
                     if (a == a || seen >= (unsigned)nblk) break;
                     if ((spin & 63) == 63) seen = ld_acquire_u32(ready);
                 }
-            } else a = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
+            }
+            // every delivery is awaited (it may be one this step has no use for) and its slot re-armed
+#pragma unroll
+            for (int d = 1; d <= TSV_MB; ++d)
+                if (delivered(d)) {
+                    float w = mb[d - 1][tid];
+                    for (int spin = 0; spin < (1 << 20) && w != w; ++spin) w = mb[d - 1][tid];
+                    mb[d - 1][tid] = __int_as_float(0x7fffffff);
+                }
 #pragma unroll
             for (int g = 0; g < 8; ++g) a -= s_part[g][tid];
             s_acc[tid] = a;
@@ -224,6 +297,15 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             } else {
                 st_relaxed_f1(ysol + row, v);
             }
+            if (use_mbox) {  // hand the block to the owners of the next steps through their shared memory
+#pragma unroll
+                for (int d = 1; d <= TSV_MB; ++d)
+                    if (crank + d < csize && s + d < s_end) {
+                        unsigned remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(&mbox[kown & 1][d - 1][tid])), "r"(crank + d));
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+                    }
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -231,6 +313,7 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             st_release_u32(ready, (unsigned)(s + 1));
         }
     }
+    if (use_mbox) ptx::cluster_sync_all();  // no CTA leaves while a neighbour may still store into its mailbox
 }
 
 }  // namespace
@@ -257,7 +340,8 @@ int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float*
 int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
                     int mode, cudaStream_t st) {
-    static int max_grid = 0;
+    static int max_grid = 0, max_grid_cl = 0;
+    constexpr int CL = 8;
     if (!max_grid) {
         cudaError_t e = cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSV_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
@@ -268,6 +352,19 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
         max_grid = sms * per_sm;
+        // co-resident clusters of CL CTAs (the mailbox hand-off); 0 = not available, use the plain launch
+        const char* env = getenv("MPLU_TSV_CLUSTER");
+        if (!(env && env[0] == '0')) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(CL); q.blockDim = dim3(TSV_THREADS); q.dynamicSmemBytes = TSV_SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, lu_solve_kernel, &q) == cudaSuccess && ncl > 0) max_grid_cl = ncl * CL;
+            else cudaGetLastError();
+        }
     }
     int nblk = npad / DBS;
     int s_begin = mode == 2 ? nblk : 0, s_end = mode == 1 ? nblk : 2 * nblk;
@@ -275,12 +372,37 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
     // NaN-fill what this launch produces: consumers poll the data (mode 2 takes its right-hand side in ysol)
     if (mode != 2) cudaMemsetAsync(ysol, 0xFF, (size_t)npad * sizeof(float), st);
     if (mode != 1 && xsol) cudaMemsetAsync(xsol, 0xFF, (size_t)npad * sizeof(float), st);
-    const int grid = nblk < max_grid ? nblk : max_grid;
-    void* args[] = {(void*)&W, (void*)&ldw, (void*)&n, (void*)&nblk, (void*)&Linv32, (void*)&Uinv32, (void*)&rhs,
-                    (void*)&ysol, (void*)&xsol, (void*)&d_out, (void*)&x_accum, (void*)&ready, (void*)&s_begin,
-                    (void*)&s_end};
-    return (int)cudaLaunchCooperativeKernel((void*)lu_solve_kernel, dim3(grid), dim3(TSV_THREADS), args, TSV_SMEM_BYTES,
-                                            st);
+    int use_mbox = 0;
+    int grid = nblk < max_grid ? nblk : max_grid;
+    if (max_grid_cl >= CL && nblk >= CL) {
+        int g = nblk < max_grid_cl ? nblk : max_grid_cl;
+        g -= g % CL;
+        if (g >= CL) { grid = g; use_mbox = 1; }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TSV_THREADS);
+    cfg.dynamicSmemBytes = TSV_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = CL; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = use_mbox ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out,
+                                        x_accum, ready, s_begin, s_end, use_mbox);
+    if (le != cudaSuccess && use_mbox) {  // cooperative cluster launch not available: plain cooperative launch from now on
+        cudaGetLastError();
+        max_grid_cl = 0;
+        use_mbox = 0;
+        cfg.gridDim = dim3(nblk < max_grid ? nblk : max_grid);
+        cfg.numAttrs = 1;
+        le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out, x_accum, ready,
+                                s_begin, s_end, use_mbox);
+    }
+    return (int)le;
 }
 
 }  // namespace mplu
