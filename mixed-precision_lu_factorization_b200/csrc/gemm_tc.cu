@@ -107,12 +107,22 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
 
 template <int kCG, bool kAMN, bool kRagged>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-               const __grid_constant__ GemmParams p0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p1) {
-    // Up to two independent problems share one launch ("grouped"): tiles [0, tiles0) belong to problem 0, the rest to
-    // problem 1 (p1.M == 0: none).  The panel code pairs the L-side and U-side products of one recursion node, which
-    // halves the number of dependent launches on the factorization's critical path.
+gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
+    // Up to kMaxGroup independent problems share one launch ("grouped"): tiles [tile_end[i-1], tile_end[i]) belong to
+    // problem i.  The panel code groups the L-side and U-side products of one recursion node (and the node's Schur
+    // update with the first products of its inverse merge), which cuts the number of dependent launches on the
+    // factorization's critical path from 7 to 3 per node.
+    const GemmParams& p0 = G.p[0];
+    auto problem_of = [&](int t) {
+        int i = 0;
+        while (i + 1 < G.count && t >= G.tile_end[i]) ++i;
+        return i;
+    };
+    auto tile_of = [&](int t, int i, int& mt, int& nt) {
+        const GemmParams& p = G.p[i];
+        const int nm = (p.M + BM * kCG - 1) / (BM * kCG), nn = (p.N + BN - 1) / BN;
+        tile_coords(t - (i ? G.tile_end[i - 1] : 0), nm, nn, mt, nt);
+    };
     using C = Cfg<kCG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -133,11 +143,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::griddep_launch();  // the stream successor may start its prologue now (it blocks in its own griddep_wait)
 
     if (warp == EPI_WARPS && lane == 0) {
-        ptx::prefetch_tmap(&tmA0);
-        ptx::prefetch_tmap(&tmB0);
-        if (p1.M > 0) {
-            ptx::prefetch_tmap(&tmA1);
-            ptx::prefetch_tmap(&tmB1);
+        for (int i = 0; i < G.count; ++i) {
+            ptx::prefetch_tmap(&G.tmA[i]);
+            ptx::prefetch_tmap(&G.tmB[i]);
         }
         for (int i = 0; i < C::STAGES; ++i) {
             ptx::mbar_init(&full[i], kCG);  // one producer arrival per CTA of the pair (leader's barrier is used)
@@ -158,10 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // nothing above touched global memory: with a programmatic launch the prologue overlapped the predecessor
     ptx::griddep_wait();
 
-    const int num_m0 = (p0.M + BM * kCG - 1) / (BM * kCG), num_n0 = (p0.N + BN - 1) / BN;
-    const int num_m1 = (p1.M + BM * kCG - 1) / (BM * kCG), num_n1 = (p1.N + BN - 1) / BN;
-    const int tiles0 = num_m0 * num_n0;
-    const int num_tiles = tiles0 + (p1.M > 0 ? num_m1 * num_n1 : 0);
+    const int num_tiles = G.tile_end[G.count - 1];
     const int first_tile = blockIdx.x / kCG;
     const int tile_step = gridDim.x / kCG;
 
@@ -170,12 +175,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = first_tile; t < num_tiles; t += tile_step) {
-                const bool second = t >= tiles0;
-                const GemmParams& p = second ? p1 : p0;
-                const CUtensorMap& tmA = second ? tmA1 : tmA0;
-                const CUtensorMap& tmB = second ? tmB1 : tmB0;
+                const int pi = problem_of(t);
+                const GemmParams& p = G.p[pi];
+                const CUtensorMap& tmA = G.tmA[pi];
+                const CUtensorMap& tmB = G.tmB[pi];
                 int mt, nt;
-                if (second) tile_coords(t - tiles0, num_m1, num_n1, mt, nt); else tile_coords(t, num_m0, num_n0, mt, nt);
+                tile_of(t, pi, mt, nt);
                 const int m0 = mt * BM * kCG + cta_rank * BM;
                 const int n0 = nt * BN + cta_rank * C::LOAD_BN;
                 const int num_kb = p.K / BK;
@@ -218,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t idesc = make_idesc_f16(BM * kCG, BN, p0.bf16 != 0, kAMN, false);
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int t = first_tile; t < num_tiles; t += tile_step, ++iter) {
-                const int num_kb = (t >= tiles0 ? p1.K : p0.K) / BK;
+                const int num_kb = G.p[problem_of(t)].K / BK;
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
@@ -280,8 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 if ((i & 3) == 0) {
                     const int t = first_tile + (i >> 2) * tile_step;
                     int mt, nt;
-                    if (t >= tiles0) { lp = &p1; tile_coords(t - tiles0, num_m1, num_n1, mt, nt); }
-                    else { lp = &p0; tile_coords(t, num_m0, num_n0, mt, nt); }
+                    const int pi = problem_of(t);
+                    lp = &G.p[pi];
+                    tile_of(t, pi, mt, nt);
                     t_row0 = mt * BM * kCG + cta_rank * BM + q * 32;
                     t_colbase = nt * BN + half * 128;
                     l_alpha = lp->alpha;
@@ -358,14 +364,15 @@ EncodeFn get_encode_fn() {
 }
 
 template <int kCG, bool kAMN, bool kRagged>
-int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, const CUtensorMap* tmA1,
-                   const CUtensorMap* tmB1, const GemmParams& p1, int max_sms, cudaStream_t stream) {
+int launch_variant(GemmGroup& g, int max_sms, cudaStream_t stream) {
     using C = Cfg<kCG>;
     auto kern = gemm_tc_kernel<kCG, kAMN, kRagged>;
-    const int num_m = (p.M + BM * kCG - 1) / (BM * kCG);
-    const int num_n = (p.N + BN - 1) / BN;
-    long long want = (long long)num_m * num_n * kCG;
-    if (p1.M > 0) want += (long long)((p1.M + BM * kCG - 1) / (BM * kCG)) * ((p1.N + BN - 1) / BN) * kCG;
+    long long tiles = 0;
+    for (int i = 0; i < g.count; ++i) {
+        tiles += (long long)((g.p[i].M + BM * kCG - 1) / (BM * kCG)) * ((g.p[i].N + BN - 1) / BN);
+        g.tile_end[i] = (int)tiles;
+    }
+    long long want = tiles * kCG;
     int grid = (int)(want < max_sms ? want : max_sms);
     grid -= grid % kCG;
     if (grid < kCG) grid = kCG;
@@ -383,8 +390,8 @@ int launch_variant(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmPar
     attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = p.pdl ? 2 : 1;
-    return (int)cudaLaunchKernelEx(&cfg, kern, *tmA, *tmB, p, *tmA1, *tmB1, p1);
+    cfg.numAttrs = g.p[0].pdl ? 2 : 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, g);
 }
 
 template <int kCG, bool kAMN, bool kRagged>
@@ -432,18 +439,13 @@ void gemm_box_shapes(int variant, uint32_t* a_box_rows, uint32_t* a_box_cols, ui
     *b_box_cols = cg2 ? BN / 2 : BN;
 }
 
-int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p,
-                    const CUtensorMap* tmA1, const CUtensorMap* tmB1, const GemmParams* p1_or_null, int max_sms,
-                    cudaStream_t stream) {
-    if (p.M <= 0 || p.N <= 0) return 0;
-    if (p.K <= 0 || p.K % BK != 0) return (int)cudaErrorInvalidValue;
-    GemmParams p1{};
-    if (p1_or_null && p1_or_null->M > 0 && p1_or_null->N > 0) {
-        p1 = *p1_or_null;
-        if (p1.K <= 0 || p1.K % BK != 0 || p1.bf16 != p.bf16) return (int)cudaErrorInvalidValue;
-    } else {
-        tmA1 = tmA;
-        tmB1 = tmB;
+int launch_gemm_group(int variant, GemmGroup& g, int max_sms, cudaStream_t stream) {
+    if (g.count <= 0 || g.count > kMaxGroup) return (int)cudaErrorInvalidValue;
+    bool ragged = false;
+    for (int i = 0; i < g.count; ++i) {
+        const GemmParams& p = g.p[i];
+        if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.K % BK != 0 || p.bf16 != g.p[0].bf16) return (int)cudaErrorInvalidValue;
+        ragged = ragged || (p.M % 32) || (p.N % 32) || (p.H && (p.h_cols % 32) && p.h_cols < p.N);
     }
     if (max_sms <= 0) {
         static int sms = 0;
@@ -455,26 +457,36 @@ int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB,
         max_sms = sms;
     }
     // aligned fast path: whole 32 x 32 epilogue chunks (the factorization only ever issues these)
-    auto is_ragged = [](const GemmParams& g) {
-        return (g.M % 32) || (g.N % 32) || (g.H && (g.h_cols % 32) && g.h_cols < g.N);
-    };
-    const bool ragged = is_ragged(p) || (p1.M > 0 && is_ragged(p1));
     if (!ragged) {
         switch (variant) {
-            case GEMM_CG1_AMN: return launch_variant<1, true, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-            case GEMM_CG2_AMN: return launch_variant<2, true, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-            case GEMM_CG1_AK: return launch_variant<1, false, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-            case GEMM_CG2_AK: return launch_variant<2, false, false>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+            case GEMM_CG1_AMN: return launch_variant<1, true, false>(g, max_sms, stream);
+            case GEMM_CG2_AMN: return launch_variant<2, true, false>(g, max_sms, stream);
+            case GEMM_CG1_AK: return launch_variant<1, false, false>(g, max_sms, stream);
+            case GEMM_CG2_AK: return launch_variant<2, false, false>(g, max_sms, stream);
             default: return (int)cudaErrorInvalidValue;
         }
     }
     switch (variant) {
-        case GEMM_CG1_AMN: return launch_variant<1, true, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-        case GEMM_CG2_AMN: return launch_variant<2, true, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-        case GEMM_CG1_AK: return launch_variant<1, false, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
-        case GEMM_CG2_AK: return launch_variant<2, false, true>(tmA, tmB, p, tmA1, tmB1, p1, max_sms, stream);
+        case GEMM_CG1_AMN: return launch_variant<1, true, true>(g, max_sms, stream);
+        case GEMM_CG2_AMN: return launch_variant<2, true, true>(g, max_sms, stream);
+        case GEMM_CG1_AK: return launch_variant<1, false, true>(g, max_sms, stream);
+        case GEMM_CG2_AK: return launch_variant<2, false, true>(g, max_sms, stream);
         default: return (int)cudaErrorInvalidValue;
     }
+}
+
+int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p,
+                    const CUtensorMap* tmA1, const CUtensorMap* tmB1, const GemmParams* p1_or_null, int max_sms,
+                    cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0) return 0;
+    GemmGroup g;
+    g.count = 1;
+    g.tmA[0] = *tmA; g.tmB[0] = *tmB; g.p[0] = p;
+    if (p1_or_null && p1_or_null->M > 0 && p1_or_null->N > 0) {
+        g.count = 2;
+        g.tmA[1] = *tmA1; g.tmB[1] = *tmB1; g.p[1] = *p1_or_null;
+    }
+    return launch_gemm_group(variant, g, max_sms, stream);
 }
 
 int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,

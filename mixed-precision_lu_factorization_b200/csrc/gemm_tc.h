@@ -57,6 +57,18 @@ int gemm_tc_init();
 int launch_gemm_tc(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p, int max_sms,
                    cudaStream_t stream);
 
+// A launch carries up to kMaxGroup independent problems of the same variant and element type; the tiles of problem i+1
+// follow those of problem i in the persistent tile order.
+constexpr int kMaxGroup = 4;
+struct alignas(64) GemmGroup {
+    CUtensorMap tmA[kMaxGroup];
+    CUtensorMap tmB[kMaxGroup];
+    GemmParams p[kMaxGroup];
+    int tile_end[kMaxGroup];  // prefix sums of the problems' tile counts (filled by the launcher)
+    int count;
+};
+int launch_gemm_group(int variant, GemmGroup& g, int max_sms, cudaStream_t stream);
+
 // Grouped launch: a second, independent problem (same variant and element type) rides in the same kernel; its tiles
 // follow the first problem's.  p1 == nullptr (or empty) degenerates to launch_gemm_tc.
 int launch_gemm_tc2(int variant, const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmParams& p,

@@ -164,6 +164,36 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
                            cg2 ? &g1.B->mapB2 : &g1.B->mapB1, &p1, lane_sms(c, ln), ln.st);
 }
 
+// Up to kMaxGroup independent products in ONE launch; falls back to separate launches when their tile variants differ.
+int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int count) {
+    GemmGroup g;
+    g.count = 0;
+    int variant = -1;
+    bool uniform = c->opts.group != 0;
+    for (int i = 0; i < count; ++i) {
+        if (calls[i].M <= 0 || calls[i].N <= 0 || calls[i].K <= 0) continue;
+        const int v = pick_variant(c, calls[i]);
+        if (variant < 0) variant = v;
+        if (v != variant) uniform = false;
+    }
+    if (variant < 0) return 0;
+    if (!uniform) {
+        for (int i = 0; i < count; ++i) CKI(run_gemm(c, ln, calls[i]));
+        return 0;
+    }
+    const bool cg2 = (variant == GEMM_CG2_AMN);
+    for (int i = 0; i < count; ++i) {
+        if (calls[i].M <= 0 || calls[i].N <= 0 || calls[i].K <= 0) continue;
+        g.tmA[g.count] = calls[i].A->mapA;
+        g.tmB[g.count] = cg2 ? calls[i].B->mapB2 : calls[i].B->mapB1;
+        g.p[g.count] = gemm_params(c, calls[i]);
+        g.count++;
+    }
+    c->gemm_launches++;
+    c->kernel_launches++;
+    return launch_gemm_group(variant, g, lane_sms(c, ln), ln.st);
+}
+
 inline int split_width(int w) { return kDiagBlock * ((w / kDiagBlock + 1) / 2); }
 
 struct Sched {
@@ -220,18 +250,22 @@ struct Sched {
         const int h = split_width(w), g = w - h, c1 = c0 + h;
         CKI(getrf(ln, T, c0, h));
         CKI(trsm_lu(ln, T, c0, h, c1, c0 + w));
-        CKI(schur(ln, c1, c0 + w, c1, c0 + w, c0, c1, g, g));
+        // The Schur update and the first products of the inverse merge,
+        //     inv(L)21 = -inv(Lb) * (L21 * inv(La)),   inv(U)12 = -(inv(Ua) * U12) * inv(Ub),
+        // only need the panel solves' results: one grouped launch.  The parked products live in a per-width slice of
+        // the scratch (columns [cap - w, cap - w + w/2)): the right child's own merges use slices further right.
+        const long long off = ldi - w;
+        GemmCall first[3] = {
+            schur_call(c1, c0 + w, c1, c0 + w, c0, c1, g, g),
+            GemmCall{&c->opFh, c1, c0, &c->opLinv, c0 - T, c0, g, h, h, nullptr, 0, false,
+                     c->Tb1 + off * ldi, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L)},
+            GemmCall{&c->opUinv, c0 - T, c0, &c->opFh, c0, c1, h, g, h, nullptr, 0, false,
+                     c->Tb2 + off * ldi, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L)}};
+        CKI(run_gemm_group(c, ln, first, 3));
         CKI(getrf(ln, T, c1, g));
-        // merge the inverses:  inv(L)21 = -inv(Lb) * (L21 * inv(La)),  inv(U)12 = -(inv(Ua) * U12) * inv(Ub);
-        // the L-side and U-side products are independent and share launches
-        GemmCall tl{&c->opFh, c1, c0, &c->opLinv, c0 - T, c0, g, h, h, nullptr, 0, false,
-                    c->Tb1, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L)};
-        GemmCall tu{&c->opUinv, c0 - T, c0, &c->opFh, c0, c1, h, g, h, nullptr, 0, false,
-                    c->Tb2, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L)};
-        CKI(run_gemm_pair(c, ln, tl, tu));
-        GemmCall x{&c->opLinv, c1 - T, c1, &c->opT1, 0, 0, g, h, g, nullptr, 0, false,
+        GemmCall x{&c->opLinv, c1 - T, c1, &c->opT1, 0, (int)off, g, h, g, nullptr, 0, false,
                    c->Linv16 + (c1 - T) + (long long)c0 * ldi, ldi, g, h, -1.f, ts(T) + 1, sc(SC_L_INV), ts(T) + 0};
-        GemmCall y{&c->opT2, 0, 0, &c->opUinv, c1 - T, c1, h, g, g, nullptr, 0, false,
+        GemmCall y{&c->opT2, 0, (int)off, &c->opUinv, c1 - T, c1, h, g, g, nullptr, 0, false,
                    c->Uinv16 + (c0 - T) + (long long)c1 * ldi, ldi, h, g, -1.f, sc(SC_L_INV), ts(T) + 3, ts(T) + 2};
         return run_gemm_pair(c, ln, x, y);
     }
@@ -340,12 +374,17 @@ int enqueue_factorization(mplu_context* c) {
     const int NB = effective_nb(c, npad);
     if ((npad + NB - 1) / NB >= mplu_context::kMaxSteps) return MPLU_E_ARG;
     cudaStream_t st = c->stream;
-    int side_sms = c->opts.side_sms > 0 ? c->opts.side_sms : 32;
+    int side_sms = c->opts.side_sms > 0 ? c->opts.side_sms : 40;
     side_sms -= side_sms % 2;
     const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && npad > 2 * NB;
     const Lane all{st, 0};
-    const Lane bulk = two ? Lane{st, c->num_sms - side_sms} : all;
-    const Lane chain = two ? Lane{c->side, side_sms} : all;
+    Lane bulk = two ? Lane{st, c->num_sms - side_sms} : all;
+    Lane chain = two ? Lane{c->side, side_sms} : all;
+    // While the trailing matrix is large the schedule is bound by the bulk lane (the chain lane waits for it), so the
+    // chain gets fewer SMs there: side_sms_early while more than early_frac of the columns remain.
+    int side_early = c->opts.side_sms_early > 0 ? c->opts.side_sms_early : side_sms;
+    side_early -= side_early % 2;
+    if (side_early < 2 || side_early > side_sms) side_early = side_sms;
     const Sched S{c, ld, (long long)c->cap_nb};
     enum { EV_GETRF = 0, EV_NEXT = 1, EV_B2 = 2, EV_B3A = 3 };
     cudaEvent_t ev = nullptr;
@@ -372,6 +411,11 @@ int enqueue_factorization(mplu_context* c) {
         const int k1 = k0 + NB;
         const int k2 = (k1 + NB < npad) ? k1 + NB : npad;
         const int nbn = k2 - k1;
+        if (two) {
+            const int sd = (npad - k2) * 100ll > (long long)npad * c->opts.early_pct ? side_early : side_sms;
+            bulk.sms = c->num_sms - sd;
+            chain.sms = sd;
+        }
         // ---- chain lane: panel solves restricted to the next tile, its Schur update, its GETRF
         if (two && step > 0) {  // tile rows/columns k1.. of block column/row k were updated by the bulk lane
             CKI(step_event(c, step - 1, EV_B2, &ev));
@@ -450,7 +494,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     }
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
-                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8),
+                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16),
                                c->W, c->tile ? (const void*)c->tile->W : nullptr};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
@@ -593,7 +637,7 @@ void mplu_default_options(mplu_options* o) {
     o->a_exp = 11;
     o->l_exp = 11;
     o->lookahead = 1;
-    o->side_sms = 32;
+    o->side_sms = 40;
     o->use_graph = 1;
     o->pdl = 0;
     o->group = 1;
@@ -604,6 +648,8 @@ void mplu_default_options(mplu_options* o) {
     o->tile_ws = 0;
     o->l2_persist = 0;
     o->cg2_min_elems = 2048 * 2048;
+    o->side_sms_early = 16;
+    o->early_pct = 55;
 }
 
 int mplu_create(mplu_context** out, int device) {
