@@ -143,6 +143,38 @@ def test_full_size_properties_n32768(mplu, solver):
     assert d["converged"] == 1 and d["status_bits"] == 0 and d["iters"] <= 3
     assert d["backward_error"] <= 1e-15 * n
     assert (x - 1).abs().max().item() <= 1e-11
+    # the backward error recomputed independently (torch fp64 GEMV) agrees with the solver's own figure
+    import torch
+    r = b - A @ x
+    be = (r.abs().max() / (A.abs().sum(dim=1).max() * x.abs().max() + b.abs().max())).item()
+    assert be <= 1e-15 * n and be <= 8 * d["backward_error"] + 1e-15  # both are rounding noise of an n-term fp64 sum
+    # linearity: same factors, right-hand side 2b - 3e_0 -> 2x - 3 A^-1 e_0, checked through its residual
+    b2 = 2.0 * b
+    b2[0] -= 3.0
+    x2 = torch.empty_like(x)
+    st2 = solver.solve_ptr(A.data_ptr(), A.stride(1), b2.data_ptr(), x2.data_ptr())
+    r2 = b2 - A @ x2
+    assert st2.converged == 1
+    assert (r2.abs().max() / (A.abs().sum(dim=1).max() * x2.abs().max() + b2.abs().max())).item() <= 1e-15 * n
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_config2_n8192_factors_reproduce_A(mplu, solver, precision):
+    """BASELINE.json configs[1] (n=8192, fp16 panel + fp16/fp32-accumulate GEMM + fp64 IR): L*U reproduces A to the
+    16-bit operand tolerance, the refined solution to fp64."""
+    import torch
+    n = 8192
+    A, b = mplu.generate(n, seed=3)
+    x, st = solver.gesv(A, b, mplu.default_options(precision=precision))
+    assert st.converged == 1 and st.iters <= 3 and st.backward_error <= 1e-15 * n
+    assert (x - 1).abs().max().item() <= 1e-11
+    LU = solver.factors(n)
+    L = torch.tril(LU, -1) + torch.eye(n, dtype=torch.float64, device="cuda")
+    U = torch.triu(LU)
+    E = (L @ U - A).abs().max().item()
+    u16 = 2.0 ** -11 if precision == 0 else 2.0 ** -8
+    # |A - LU| <= c * u16 * max|A| with a modest constant: the diagonal of this matrix is ~n/2 * 10
+    assert E <= 0.05 * u16 * A.abs().max().item(), E
 
 
 # ---- condition-number sweep (BASELINE.json configs[4]) and GMRES-based refinement -----------------------------------
