@@ -412,9 +412,15 @@ int enqueue_factorization(mplu_context* c) {
         const int k2 = (k1 + NB < npad) ? k1 + NB : npad;
         const int nbn = k2 - k1;
         if (two) {
-            const int sd = (npad - k2) * 100ll > (long long)npad * c->opts.early_pct ? side_early : side_sms;
+            const long long rem100 = (npad - k2) * 100ll;
+            const int sd = rem100 > (long long)npad * c->opts.early_pct ? side_early : side_sms;
             bulk.sms = c->num_sms - sd;
             chain.sms = sd;
+            if (rem100 <= (long long)npad * c->opts.late_pct) {
+                // the trailing matrix is small: the bulk lane idles most of the step, both lanes may use every SM
+                bulk.sms = 0;
+                chain.sms = 0;
+            }
         }
         // ---- chain lane: panel solves restricted to the next tile, its Schur update, its GETRF
         if (two && step > 0) {  // tile rows/columns k1.. of block column/row k were updated by the bulk lane
@@ -494,7 +500,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     }
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
-                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16),
+                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8),
                                c->W, c->tile ? (const void*)c->tile->W : nullptr};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
@@ -650,6 +656,7 @@ void mplu_default_options(mplu_options* o) {
     o->cg2_min_elems = 2048 * 2048;
     o->side_sms_early = 16;
     o->early_pct = 55;
+    o->late_pct = 35;
 }
 
 int mplu_create(mplu_context** out, int device) {
