@@ -172,6 +172,22 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when it initialises; the contract is ONE JSON line on stdout, so the
+    communicator set-up runs with file descriptor 1 pointed at stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_distributed(args, m, pk, rank, world, local):
     """N > 1: ONE n x n system, 2D block-cyclic over a P x Q grid (one process per GPU, NCCL over NVLink)."""
     import torch
@@ -179,11 +195,14 @@ def run_distributed(args, m, pk, rank, world, local):
     n = args.n or 131072
     nb = args.nb or 2048
     P, Q = m.grid_shape(world)
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid = torch.tensor(list(m.DistSolver.unique_id()), dtype=torch.uint8, device="cuda")
-    dist.broadcast(uid, 0)
-    ds = m.DistSolver(local, P, Q, rank=rank, unique_id=bytes(uid.cpu().tolist()))
+    with stdout_to_stderr():
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(m.DistSolver.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        ds = m.DistSolver(local, P, Q, rank=rank, unique_id=bytes(uid.cpu().tolist()))
+        dist.barrier()
+        torch.cuda.synchronize()
     opts = m.default_options(precision=1 if args.precision == "bf16" else 0)
     As, bs = ds.generate(n, nb, seed=1)
     p, q, mloc, nloc = ds.local_shape(0, n, nb)
@@ -270,7 +289,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=0, help="matrix order (default: 32768 on 1 GPU, 131072 block-cyclic on N > 1)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0,
+                    help="matrix order (default: 32768 on 1 GPU, 131072 block-cyclic on N > 1); under torchrun spell it --size (torchrun rejects --n as an ambiguous prefix of its own options)")
     ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default for this n)")
     ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
     ap.add_argument("--impl", choices=["mplu", "reference"], default="mplu")
@@ -295,7 +315,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = importlib.import_module(PKG_NAME)
     pk = peaks()
     if world > 1:
