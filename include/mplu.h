@@ -58,6 +58,7 @@ typedef struct mplu_options {
     int cg2_min_elems;/* MPLU_GEMM_AUTO: products with M*N below this use single-CTA tiles even when M > 128 */
     int side_sms_early; /* chain-lane SMs while more than early_pct % of the columns are still trailing (0 = side_sms) */
     int early_pct;
+    int tri_skip;     /* 1 (default): products with an explicit triangular inverse skip the zero half of their K range */
     int late_pct;     /* once at most late_pct % of the columns are trailing, both lanes may use every SM */
     int l2_persist;   /* 1: with tile_ws, pin that workspace in L2 through an access-policy window on the chain lane's
                          stream (default 0: measured much slower, 62.6 ms -- the carve-out starves the trailing GEMM) */

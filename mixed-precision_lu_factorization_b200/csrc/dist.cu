@@ -569,7 +569,8 @@ int enqueue_dist_factorization(mplu_dist* d) {
                 const long long jk = k / Q;
                 GemmCall g{&r.opWh, (int)(ilo * nb), (int)(jk * nb), &r.opInvU[b], 0, 0, (int)rows, nb, nb,
                            r.W + (long long)ilo * nb + jk * nb * r.mloc, r.mloc, false,
-                           r.Lp[b], rows, (int)rows, nb, 1.f, r.ctx->scales + SC_A_INV, r.tsc[b] + 3, r.ctx->scales + SC_L};
+                           r.Lp[b], rows, (int)rows, nb, 1.f, r.ctx->scales + SC_A_INV, r.tsc[b] + 3, r.ctx->scales + SC_L,
+                           TRI_B_UPPER};
                 CKI(run_gemm(r.ctx, ln, g));
             }
             if (r.p == pk && cols > 0) {
@@ -577,7 +578,7 @@ int enqueue_dist_factorization(mplu_dist* d) {
                 GemmCall g{&r.opInvL[b], 0, 0, &r.opWh, (int)(ik * nb), (int)(jlo * nb), nb, (int)cols, nb,
                            r.W + ik * nb + (long long)jlo * nb * r.mloc, r.mloc, false,
                            r.Up[b] + (long long)jlo * nb * nb, nb, nb, (int)cols, 1.f, r.tsc[b] + 1,
-                           r.ctx->scales + SC_A_INV, r.ctx->scales + SC_A};
+                           r.ctx->scales + SC_A_INV, r.ctx->scales + SC_A, TRI_A_LOWER};
                 CKI(run_gemm(r.ctx, ln, g));
             }
         }

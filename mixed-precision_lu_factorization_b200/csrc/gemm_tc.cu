@@ -118,6 +118,17 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         while (i + 1 < G.count && t >= G.tile_end[i]) ++i;
         return i;
     };
+    // k-block range [kb0, kb1) of a tile: everything, or the part where a triangular operand is non-zero
+    auto k_range = [&](const GemmParams& p, int mt, int nt, int& kb0, int& kb1) {
+        int k0 = 0, k1 = p.K;
+        const int mlo = mt * BM * kCG, mhi = mlo + BM * kCG, nlo = nt * BN, nhi = nlo + BN;
+        if (p.tri == TRI_A_LOWER) k1 = min(p.K, mhi);
+        else if (p.tri == TRI_A_UPPER) k0 = min(mlo, p.K - BK);
+        else if (p.tri == TRI_B_UPPER) k1 = min(p.K, nhi);
+        else if (p.tri == TRI_B_LOWER) k0 = min(nlo, p.K - BK);
+        kb0 = k0 / BK;
+        kb1 = (k1 + BK - 1) / BK;
+    };
     auto tile_of = [&](int t, int i, int& mt, int& nt) {
         const GemmParams& p = G.p[i];
         const int nm = (p.M + BM * kCG - 1) / (BM * kCG), nn = (p.N + BN - 1) / BN;
@@ -183,8 +194,9 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                 tile_of(t, pi, mt, nt);
                 const int m0 = mt * BM * kCG + cta_rank * BM;
                 const int n0 = nt * BN + cta_rank * C::LOAD_BN;
-                const int num_kb = p.K / BK;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                int kb0, kb1;
+                k_range(p, mt, nt, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     if constexpr (kCG == 1) {
                         ptx::mbar_arrive_expect_tx(&full[stage], C::A_BYTES + C::B_BYTES);
@@ -223,12 +235,18 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
             const uint32_t idesc = make_idesc_f16(BM * kCG, BN, p0.bf16 != 0, kAMN, false);
             uint32_t stage = 0, phase = 0, iter = 0;
             for (int t = first_tile; t < num_tiles; t += tile_step, ++iter) {
-                const int num_kb = G.p[problem_of(t)].K / BK;
+                int kb0, kb1;
+                {
+                    const int pi = problem_of(t);
+                    int mt, nt;
+                    tile_of(t, pi, mt, nt);
+                    k_range(G.p[pi], mt, nt, kb0, kb1);
+                }
                 const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
                     if (lane == 0) {
@@ -246,10 +264,10 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                                 adesc = ptx::make_smem_desc_sw128(a_base + k * 32, 0, 1024);
                             }
                             bdesc = ptx::make_smem_desc_sw128(b_base + k * 32, 0, 1024);
-                            ptx::umma_f16<kCG>(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                            ptx::umma_f16<kCG>(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                         }
                         ptx::umma_commit<kCG>(&empty[stage]);
-                        if (kb == num_kb - 1) ptx::umma_commit<kCG>(&tfull[as]);
+                        if (kb == kb1 - 1) ptx::umma_commit<kCG>(&tfull[as]);
                     }
                     __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }

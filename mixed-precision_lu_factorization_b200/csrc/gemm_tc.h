@@ -13,6 +13,8 @@
 
 namespace mplu {
 
+enum GemmTri : int { TRI_NONE = 0, TRI_A_LOWER = 1, TRI_A_UPPER = 2, TRI_B_UPPER = 3, TRI_B_LOWER = 4 };
+
 enum GemmVariant : int {
     GEMM_CG1_AMN = 0,  // 1-CTA tiles 128x256, A column-major (M contiguous)
     GEMM_CG2_AMN = 1,  // CTA-pair tiles 256x256, A column-major
@@ -39,6 +41,8 @@ struct GemmParams {
     int bf16;     // 0 = fp16 operands/shadow, 1 = bf16
     int* status;  // device word; bit 0 set when a shadow value overflowed the 16-bit range
     int pdl;      // 1 = launch with programmatic stream serialization (prologue overlaps the predecessor's tail)
+    int tri;      // triangular operand: the K range of a tile is cut to the part where that operand is non-zero
+                  // (TRI_NONE, TRI_A_LOWER: A(m,k)=0 for k>m, TRI_A_UPPER: k<m, TRI_B_UPPER: B(k,n)=0 for k>n, TRI_B_LOWER: k<n)
 };
 
 // Build a 2-D TMA map (SWIZZLE_128B, 16-bit elements) over a column-major parent array with `rows` x `cols`

@@ -118,6 +118,7 @@ GemmParams gemm_params(const mplu_context* c, const GemmCall& g) {
     p.bf16 = c->opts.precision == MPLU_BF16;
     p.status = c->status;
     p.pdl = c->opts.pdl;
+    p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
     return p;
 }
 
@@ -219,7 +220,7 @@ struct Sched {
     // U[k0:k0+w, c0:c1) = inv(L[k0:k0+w)) * A[k0:k0+w, c0:c1)   (inverse of the block inside tile T, one GEMM)
     GemmCall trsm_u_call(int T, int k0, int w, int c0, int c1) const {
         return GemmCall{&c->opLinv, k0 - T, k0, &c->opWh, k0, c0, w, c1 - c0, w, Wp(k0, c0), ld, false,
-                        Fhp(k0, c0), ld, w, c1 - c0, 1.f, ts(T) + 1, sc(SC_A_INV), sc(SC_A)};
+                        Fhp(k0, c0), ld, w, c1 - c0, 1.f, ts(T) + 1, sc(SC_A_INV), sc(SC_A), TRI_A_LOWER};
     }
     int trsm_u(const Lane& ln, int T, int k0, int w, int c0, int c1) const {
         return run_gemm(c, ln, trsm_u_call(T, k0, w, c0, c1));
@@ -227,7 +228,7 @@ struct Sched {
     // L[r0:r1, k0:k0+w) = A[r0:r1, k0:k0+w) * inv(U[k0:k0+w))
     GemmCall trsm_l_call(int T, int k0, int w, int r0, int r1) const {
         return GemmCall{&c->opWh, r0, k0, &c->opUinv, k0 - T, k0, r1 - r0, w, w, Wp(r0, k0), ld, false,
-                        Fhp(r0, k0), ld, r1 - r0, w, 1.f, sc(SC_A_INV), ts(T) + 3, sc(SC_L)};
+                        Fhp(r0, k0), ld, r1 - r0, w, 1.f, sc(SC_A_INV), ts(T) + 3, sc(SC_L), TRI_B_UPPER};
     }
     int trsm_l(const Lane& ln, int T, int k0, int w, int r0, int r1) const {
         return run_gemm(c, ln, trsm_l_call(T, k0, w, r0, r1));
@@ -258,15 +259,15 @@ struct Sched {
         GemmCall first[3] = {
             schur_call(c1, c0 + w, c1, c0 + w, c0, c1, g, g),
             GemmCall{&c->opFh, c1, c0, &c->opLinv, c0 - T, c0, g, h, h, nullptr, 0, false,
-                     c->Tb1 + off * ldi, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L)},
+                     c->Tb1 + off * ldi, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L), TRI_B_LOWER},
             GemmCall{&c->opUinv, c0 - T, c0, &c->opFh, c0, c1, h, g, h, nullptr, 0, false,
-                     c->Tb2 + off * ldi, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L)}};
+                     c->Tb2 + off * ldi, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L), TRI_A_UPPER}};
         CKI(run_gemm_group(c, ln, first, 3));
         CKI(getrf(ln, T, c1, g));
         GemmCall x{&c->opLinv, c1 - T, c1, &c->opT1, 0, (int)off, g, h, g, nullptr, 0, false,
-                   c->Linv16 + (c1 - T) + (long long)c0 * ldi, ldi, g, h, -1.f, ts(T) + 1, sc(SC_L_INV), ts(T) + 0};
+                   c->Linv16 + (c1 - T) + (long long)c0 * ldi, ldi, g, h, -1.f, ts(T) + 1, sc(SC_L_INV), ts(T) + 0, TRI_A_LOWER};
         GemmCall y{&c->opT2, 0, (int)off, &c->opUinv, c1 - T, c1, h, g, g, nullptr, 0, false,
-                   c->Uinv16 + (c0 - T) + (long long)c1 * ldi, ldi, h, g, -1.f, sc(SC_L_INV), ts(T) + 3, ts(T) + 2};
+                   c->Uinv16 + (c0 - T) + (long long)c1 * ldi, ldi, h, g, -1.f, sc(SC_L_INV), ts(T) + 3, ts(T) + 2, TRI_B_UPPER};
         return run_gemm_pair(c, ln, x, y);
     }
 };
@@ -500,7 +501,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     }
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
-                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8),
+                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8) + (c->opts.tri_skip << 1),
                                c->W, c->tile ? (const void*)c->tile->W : nullptr};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
@@ -657,6 +658,7 @@ void mplu_default_options(mplu_options* o) {
     o->side_sms_early = 16;
     o->early_pct = 55;
     o->late_pct = 35;
+    o->tri_skip = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {

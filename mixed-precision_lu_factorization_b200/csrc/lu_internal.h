@@ -103,6 +103,7 @@ struct GemmCall {
     const float* alpha_p1;
     const float* alpha_p2;
     const float* hscale_p;               // H = cvt16(out * *hscale_p)
+    int tri = 0;                         // GemmTri: which operand is triangular (its zero part of K is skipped)
 };
 
 // Where a piece of the schedule runs: stream + SM budget (0 = all SMs).

@@ -223,3 +223,27 @@ def test_fp16_overflow_falls_back_to_bf16(mplu, oracle, solver):
     x2, st2 = solver.gesv(dA, db, mplu.default_options(refinement=mplu.REFINE_GMRES), allow_noconv=True)
     assert st2.precision_used == (mplu.MPLU_BF16 if overflowed else mplu.MPLU_FP16)
     assert np.isfinite(x2.cpu().numpy()).all()
+
+
+def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
+    """Grouped launches, triangular K-range skipping, lane split, CUDA graph, workspace GETRF only change WHEN and WHERE
+    the same products are formed: the factors are bit-identical."""
+    import torch
+    n = 2304  # not a multiple of the tile size: the last tile is partial
+    A = oracle.counter_matrix(n, seed=4)
+    dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
+    db = torch.tensor(A.sum(axis=1), dtype=torch.float64, device="cuda")
+    ref = None
+    s = mplu.Solver(0)
+    try:
+        for kw in (dict(), dict(group=0), dict(tri_skip=0), dict(lookahead=0), dict(use_graph=0), dict(tile_ws=1),
+                   dict(side_sms=16, side_sms_early=8), dict(gemm_variant=mplu.GEMM_CG2)):
+            x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
+            LU = s.factors(n)
+            assert st.converged == 1
+            if ref is None:
+                ref = LU.clone()
+            else:
+                assert torch.equal(LU, ref), kw
+    finally:
+        s.close()
