@@ -62,6 +62,9 @@ typedef struct mplu_options {
     int late_pct;     /* once at most late_pct % of the columns are trailing, both lanes may use every SM */
     int l2_persist;   /* 1: with tile_ws, pin that workspace in L2 through an access-policy window on the chain lane's
                          stream (default 0: measured much slower, 62.6 ms -- the carve-out starves the trailing GEMM) */
+    int stream_host;  /* mplu_gesv_host only.  1 (default): A is copied block column by block column and factored
+                         left-looking as it arrives, so the factorization hides behind the PCIe transfer (same factors
+                         bit for bit); 0: copy everything, then run the device schedule */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -22,6 +22,11 @@ constexpr int kDiagBlock = 128;  // diagonal block / base panel width
 int panel_init();  // per-device kernel attributes; call before the first launch / graph capture
 int launch_first_touch(const double* A, long long lda, int n, float* W, long long ldw, int npad, float* amax,
                        double* rowsum_part, int nchunk, double* anorm, cudaStream_t st);
+// the same first touch for the columns [cb, ce) only (amax accumulates, not reset; row sums into slots
+// [slot0, slot0 + nslots) of rowsum_part), and the final ||A||_inf over the first nslots slots
+int launch_first_touch_cols(const double* A, long long lda, int n, float* W, long long ldw, int npad, int cb, int ce,
+                            float* amax, double* rowsum_part, int slot0, int nslots, cudaStream_t st);
+int launch_anorm(const double* rowsum_part, int n, int nslots, double* anorm, cudaStream_t st);
 int launch_scales(const float* amax, float* scales, int target_exp_a, int exp_l, int bf16, cudaStream_t st);
 int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, int rows, int cols, const float* scale,
                        int bf16, int* status, cudaStream_t st);
@@ -32,7 +37,8 @@ int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, in
 int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, long long ld16, float* Linv32,
                    float* Uinv32, float* tile_scales, int first_in_tile, int blk, int bf16, int* status, cudaStream_t st,
                    long long* dbg_clk = nullptr,  // optional device array of phase time stamps (clock64)
-                   int pdl = 0);                  // 1 = programmatic dependent launch
+                   int pdl = 0,                   // 1 = programmatic dependent launch
+                   int valid = kDiagBlock);       // rows/columns of the block that belong to the matrix (the rest is identity padding)
 
 // ir.cu
 // r = b - A*x (fp64), ||r||_inf and ||x||_inf into norms[0], norms[1]

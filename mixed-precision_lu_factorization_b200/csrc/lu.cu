@@ -244,7 +244,8 @@ struct Sched {
             uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
             uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
             CKI(launch_diag_lu(c->W, ld, c0, l16, u16, ldi, c->Linv32, c->Uinv32, ts(T), c0 == T, blk,
-                               c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, c->opts.pdl));
+                               c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, c->opts.pdl,
+                               c->n - c0 < kDiagBlock ? c->n - c0 : kDiagBlock));
             c->kernel_launches++;
             return 0;
         }
@@ -540,6 +541,75 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     return 0;
 }
 
+// Host-resident input (mplu_gesv_host): the factorization runs LEFT-looking over nb-wide block columns so that it
+// overlaps the PCIe transfer, which is 4x longer than the whole device-resident solve (8 n^2 bytes at ~55 GB/s).
+// Block column j is copied on the copy stream; as soon as it has arrived the compute stream casts it (first touch),
+// brings it up to date with the j block columns factored before it -- U_kj = inv(L_kk) A_kj, A_{k+1:,j} -= L_{k+1:,k} U_kj
+// for k = 0..j-1, the reference's Dtrsm / Dgemm pair (MPF.cu:215-239) applied per arriving block column --, factors its
+// diagonal tile and solves its L panel.  Every tile receives the same products in the same order as in the
+// right-looking schedule, so the factors are bit-identical to mplu_factor_device's; what remains after the last
+// byte has arrived is the last block column's update chain and one diagonal-tile GETRF.
+// The fp16 scale has to be fixed before the first cast: it is taken from the first block column (which holds the
+// first diagonal tile); a later block column that leaves the fp16 range under that scale sets the overflow bit and
+// the caller redoes the solve from the (by then resident) device copy with the global scale.
+bool streamed_supported(const mplu_context* c, int n) {
+    const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
+    const int NB = effective_nb(c, npad);
+    const int nt = (npad + NB - 1) / NB;
+    return nt >= 2 && nt <= c->nchunk && nt < mplu_context::kMaxSteps;
+}
+
+int factor_streamed(mplu_context* c, int n, const double* hA, long long lda, double* dA) {
+    CKI(ensure_work(c, n));
+    const int npad = c->npad;
+    const long long ld = npad;
+    const int bf16 = c->opts.precision == MPLU_BF16;
+    const int NB = effective_nb(c, npad);
+    const int nt = (npad + NB - 1) / NB;
+    const int per = c->nchunk / nt;  // row-sum slots per block column
+    if (per < 1 || nt >= mplu_context::kMaxSteps) return MPLU_E_ARG;
+    cudaStream_t st = c->stream, cp = c->copy;
+    CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(c->amax, 0, sizeof(float), st));
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    c->gemm_launches = 0;
+    c->kernel_launches = 0;
+    c->trail_count = 0;
+    c->trail_flops = c->trail_bytes = 0;
+    c->mark_count = 0;
+    const Sched S{c, ld, (long long)c->cap_nb};
+    const Lane all{st, 0};
+    for (int j = 0; j < nt; ++j) {
+        const int c0 = j * NB, c1 = (c0 + NB < npad) ? c0 + NB : npad, w = c1 - c0;
+        const int real = (n < c1 ? n : c1) - c0;  // columns of A in this block column (the rest is padding)
+        if (real > 0)
+            CK(cudaMemcpy2DAsync(dA + (size_t)c0 * n, (size_t)n * sizeof(double), hA + (size_t)c0 * lda,
+                                 (size_t)lda * sizeof(double), (size_t)n * sizeof(double), real, cudaMemcpyHostToDevice, cp));
+        cudaEvent_t& e = c->ev_copy[j];
+        if (!e) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(e, cp));
+        CK(cudaStreamWaitEvent(st, e, 0));
+        CKI(launch_first_touch_cols(dA, n, n, c->W, ld, npad, c0, c1, c->amax, c->rowsum_part, j * per, per, st));
+        if (j == 0) CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+        CKI(launch_shadow_cast(c->W + (long long)c0 * ld, ld, c->Wh + (long long)c0 * ld, ld, npad, w, c->scales + SC_A,
+                               bf16, c->status, st));
+        c->kernel_launches += (j == 0) ? 3 : 2;
+        for (int k0 = 0; k0 < c0; k0 += NB) {
+            const int k1 = k0 + NB;
+            CKI(S.trsm_u(all, k0, k0, NB, c0, c1));
+            CKI(S.schur(all, k1, npad, c0, c1, k0, k1, npad - k1, w));
+        }
+        CKI(S.getrf(all, c0, c0, w));
+        if (c1 < npad) CKI(S.trsm_l(all, c0, c0, w, c1, npad));
+    }
+    c->copy_last = nt - 1;
+    CKI(launch_anorm(c->rowsum_part, n, nt * per, c->anorm, st));
+    c->kernel_launches++;
+    c->factored = true;
+    return 0;
+}
+
 __global__ void absmax_kernel(const double* v, int n, double* out) {
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, fabs(v[i]));
@@ -659,6 +729,7 @@ void mplu_default_options(mplu_options* o) {
     o->early_pct = 55;
     o->late_pct = 35;
     o->tri_skip = 1;
+    o->stream_host = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -676,6 +747,7 @@ int mplu_create(mplu_context** out, int device) {
     CKI(panel_init());
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
@@ -702,6 +774,8 @@ void mplu_destroy(mplu_context* c) {
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_step) if (e) cudaEventDestroy(e);
     for (auto& e : c->mark_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
+    if (c->copy) cudaStreamDestroy(c->copy);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -781,13 +855,46 @@ int mplu_gesv_host(mplu_context* c, int n, const double* hA, long long lda, cons
         c->dv_cap = n;
     }
     cudaStream_t st = c->stream;
+    if (opts) c->opts = *opts;
+    resolve_options(c, n);
+    const mplu_options used = c->opts;
     CK(cudaEventRecord(c->ev[3], st));
-    CK(cudaMemcpy2DAsync(c->dA_stage, (size_t)n * sizeof(double), hA, (size_t)lda * sizeof(double),
-                         (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->db_stage, hb, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = mplu_gesv_device(c, n, c->dA_stage, n, c->db_stage, c->dx_stage, opts, stats);
+    int rc;
     float h2d = 0.f;
-    cudaEventElapsedTime(&h2d, c->ev[3], c->ev[0]);
+    if (c->opts.stream_host && streamed_supported(c, n)) {
+        // block columns are factored as they arrive (factor_streamed); the staged copy of A stays for the residuals
+        if (stats) memset(stats, 0, sizeof(*stats));
+        c->factored = false;
+        CK(cudaStreamWaitEvent(c->copy, c->ev[3], 0));
+        CK(cudaMemcpyAsync(c->db_stage, hb, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = factor_streamed(c, n, hA, lda, c->dA_stage);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev[1], st));
+        rc = solve_impl(c, c->dA_stage, n, c->db_stage, c->dx_stage, stats);
+        if (stats) stats->precision_used = c->opts.precision;
+        CK(cudaEventRecord(c->ev[2], st));
+        CK(cudaEventSynchronize(c->ev[2]));
+        cudaEventElapsedTime(&h2d, c->ev[3], c->ev_copy[c->copy_last]);
+        if (stats) {
+            // total = h2d (start .. last byte on the device) + factor (the tail left after it) + solve
+            cudaEventElapsedTime(&stats->factor_ms, c->ev_copy[c->copy_last], c->ev[1]);
+            cudaEventElapsedTime(&stats->solve_ms, c->ev[1], c->ev[2]);
+            stats->total_ms = stats->factor_ms + stats->solve_ms;
+        }
+        if (rc == MPLU_E_OVERFLOW) {
+            // the scale taken from the first block column did not fit a later one: A is resident now, redo the solve
+            // with the global scale (and, if that overflows too, in bf16)
+            const float streamed_ms = h2d + (stats ? stats->total_ms : 0.f);
+            rc = mplu_gesv_device(c, n, c->dA_stage, n, c->db_stage, c->dx_stage, &used, stats);
+            h2d = streamed_ms;  // everything before the redo counts as transfer time
+        }
+    } else {
+        CK(cudaMemcpy2DAsync(c->dA_stage, (size_t)n * sizeof(double), hA, (size_t)lda * sizeof(double),
+                             (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->db_stage, hb, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        rc = mplu_gesv_device(c, n, c->dA_stage, n, c->db_stage, c->dx_stage, &used, stats);
+        cudaEventElapsedTime(&h2d, c->ev[3], c->ev[0]);
+    }
     if (rc != 0 && rc != MPLU_E_NOCONV) return rc;
     CK(cudaEventRecord(c->ev[0], st));
     CK(cudaMemcpyAsync(hx, c->dx_stage, n * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -45,6 +45,10 @@ struct mplu_context {
     // staging for the host variant
     double* dA_stage = nullptr; size_t dA_cap = 0;
     double* db_stage = nullptr; double* dx_stage = nullptr; size_t dv_cap = 0;
+    // streamed host variant: copy stream, one event per block column (ev_copy[copy_last] = last byte arrived)
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_copy[512] = {};
+    int copy_last = 0;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {
         uint16_t* base = nullptr;

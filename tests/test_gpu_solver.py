@@ -67,7 +67,7 @@ def test_ragged_sizes(mplu, oracle, solver, n):
     A = oracle.counter_matrix(n, seed=2)
     b = A @ np.linspace(-1, 1, n)
     x, st = run(mplu, solver, A, b, nb=512)
-    assert st["converged"] == 1
+    assert st["converged"] == 1 and st["status_bits"] == 0  # the identity padding must not raise the overflow bit
     np.testing.assert_allclose(x, np.linspace(-1, 1, n), rtol=0, atol=1e-11)
 
 
@@ -109,6 +109,58 @@ def test_host_buffer_entry_point(mplu, oracle, solver):
     st = solver.gesv_host_ptr(n, A.ctypes.data, n, b.ctypes.data, x.ctypes.data, mplu.default_options())
     assert st.converged == 1 and st.h2d_ms > 0
     np.testing.assert_allclose(x, 1.0, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,nb", [(2304, 512), (1000, 256), (4096, 1024)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_streamed_host_path_gives_bit_identical_factors(mplu, oracle, n, nb, pinned):
+    """mplu_gesv_host factors left-looking, block column by block column, while A is still arriving over PCIe: the same
+    products in the same order as the device schedule, hence the same factors bit for bit and the same solution;
+    stream_host=0 (copy first, then the device schedule) is the comparison."""
+    import torch
+    A = np.asfortranarray(oracle.counter_matrix(n, seed=21))
+    b = A.sum(axis=1)
+    if pinned:
+        hA = torch.empty(n, n, dtype=torch.float64, pin_memory=True)
+        hA.copy_(torch.from_numpy(np.ascontiguousarray(A.T)))  # contiguous storage of A^T = column-major A
+        hb = torch.from_numpy(b.copy()).pin_memory()
+        hx = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        pA, pb, px = hA.data_ptr(), hb.data_ptr(), hx.data_ptr()
+    else:
+        x = np.empty(n)
+        pA, pb, px = A.ctypes.data, b.ctypes.data, x.ctypes.data
+    s = mplu.Solver(0)
+    try:
+        outs = []
+        for stream_host in (1, 0, 1):
+            st = s.gesv_host_ptr(n, pA, n, pb, px, mplu.default_options(nb=nb, stream_host=stream_host))
+            assert st.converged == 1 and st.status_bits == 0 and st.h2d_ms > 0
+            xs = hx.numpy().copy() if pinned else x.copy()
+            outs.append((s.factors(n).clone(), xs, st.iters))
+        for LU, xs, it in outs[1:]:
+            assert torch.equal(LU, outs[0][0])
+            assert it == outs[0][2]
+            np.testing.assert_array_equal(xs, outs[0][1])
+        np.testing.assert_allclose(outs[0][1], 1.0, rtol=0, atol=1e-11)
+    finally:
+        s.close()
+
+
+def test_streamed_host_path_scale_overflow_is_redone(mplu, oracle):
+    """The fp16 scale of the streamed path comes from the first block column; a later block column far outside that
+    range must end in a correct solve (redo with the global scale), not in a silent overflow."""
+    n, nb = 1536, 512
+    A = np.asfortranarray(oracle.counter_matrix(n, seed=5))
+    A[:, nb:] *= 64.0  # later block columns 2^6 larger: (2^10, 2^11] * 2^6 leaves the fp16 range
+    b = A.sum(axis=1)
+    x = np.empty(n)
+    s = mplu.Solver(0)
+    try:
+        st = s.gesv_host_ptr(n, A.ctypes.data, n, b.ctypes.data, x.ctypes.data, mplu.default_options(nb=nb))
+        assert st.converged == 1
+        np.testing.assert_allclose(x, 1.0, rtol=0, atol=1e-10)
+    finally:
+        s.close()
 
 
 def test_spd_kappa_small(mplu, oracle, solver):
