@@ -34,6 +34,7 @@ enum {
 enum { MPLU_FP16 = 0, MPLU_BF16 = 1 };
 enum { MPLU_GEMM_AUTO = -1, MPLU_GEMM_CG1 = 0, MPLU_GEMM_CG2 = 1 };
 enum { MPLU_REFINE_CLASSIC = 0, MPLU_REFINE_GMRES = 1 };
+enum { MPLU_SCHED_RIGHT = 0, MPLU_SCHED_LEFT = 1 };
 
 typedef struct mplu_options {
     int precision;    /* MPLU_FP16 (default) or MPLU_BF16: panel/operand storage type; accumulation is fp32 */
@@ -47,7 +48,8 @@ typedef struct mplu_options {
     int lookahead;    /* 1 (default): factor panel k+1 on a second stream while the rest of update k runs */
     int side_sms;     /* SMs of the chain lane (diagonal-tile GETRF + next-tile solves), default 32 */
     int use_graph;    /* 1 (default): capture the factorization schedule once per (n, options) into a CUDA graph */
-    int pdl;          /* 1: programmatic dependent launches along each stream's kernel chain (default 0: measured slower, pre-launched CTAs take SMs from the other lane) */
+    int pdl;          /* 1: programmatic dependent launches along each stream's kernel chain (default 0: measured slower,
+                         pre-launched CTAs take SMs from the other lane); 2: on the chain lane only */
     int group;        /* 1 (default): independent L-side / U-side products of a recursion node share one launch */
     int refinement;   /* MPLU_REFINE_CLASSIC (default): d = (LU)^-1 r;  MPLU_REFINE_GMRES: GMRES on (LU)^-1 A d = (LU)^-1 r */
     int gmres_restart;/* Krylov steps per correction at most (default 50) */
@@ -65,6 +67,15 @@ typedef struct mplu_options {
     int stream_host;  /* mplu_gesv_host only.  1 (default): A is copied block column by block column and factored
                          left-looking as it arrives, so the factorization hides behind the PCIe transfer (same factors
                          bit for bit); 0: copy everything, then run the device schedule */
+    int schedule;     /* device-resident input: MPLU_SCHED_LEFT (default) = left-looking block columns with look-ahead and
+                         eager updates, MPLU_SCHED_RIGHT = right-looking trailing updates with depth-1 look-ahead
+                         (same factors bit for bit; n=32768: 35.8 vs 38.3 ms) */
+    int eager;        /* MPLU_SCHED_LEFT: 1 (default) = the bulk lane spends each step's share of the remaining update work
+                         ahead of need on the columns further right (balances the lanes); 0 = strictly left-looking */
+    int side_sms_left;/* MPLU_SCHED_LEFT: SMs of the chain lane (default 32; side_sms / side_sms_early are the right-looking
+                         schedule's) */
+    int stream_c;     /* 1 (default): the tall rank-nb updates load / store their fp32 C and 16-bit shadow with the streaming
+                         (evict-first) cache policy: that traffic is touched once per launch and far larger than L2 */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -53,7 +53,10 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mt
 // 25-35 us on a cold instruction cache (gpurun_out/launches_r01b_n16384.csv).  kRagged = per-element bounds checks
 // (arbitrary M, N: the mplu_gemm16 hook); otherwise M % 32 == 0, N % 32 == 0, h_cols % 32 == 0 and a chunk is
 // either entirely inside the matrix or entirely outside (warp-uniform test, no per-element predicates).
-template <bool kRagged>
+// kStream: the fp32 addend / result and the 16-bit shadow are touched once per launch and far larger than L2 (the bulk
+// lane's tall rank-nb updates): load / store them with the streaming (evict-first) cache policy so that they do not
+// push the operand panels -- and the chain lane's diagonal tile -- out of L2.
+template <bool kRagged, bool kStream>
 __device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, int row, int col0, bool ok) {
     const float* src = p.Cin + row + (long long)col0 * p.ldcin;
     if constexpr (kRagged) {
@@ -62,12 +65,12 @@ __device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, 
     } else {
         if (ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = src[(long long)j * p.ldcin];
+            for (int j = 0; j < 32; ++j) dst[j] = kStream ? __ldcs(src + (long long)j * p.ldcin) : src[(long long)j * p.ldcin];
         }
     }
 }
 
-template <bool kRagged>
+template <bool kRagged, bool kStream>
 __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (&cin)[32], const GemmParams& p,
                                           float alpha, float hs, int row, int col0, bool ok, float& mx) {
     if (!kRagged && !ok) return;
@@ -78,7 +81,10 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
         float* dst = p.C + row + (long long)col0 * p.ldc;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            if (!kRagged || (row < p.M && col0 + j < p.N)) dst[(long long)j * p.ldc] = out[j];
+            if (!kRagged || (row < p.M && col0 + j < p.N)) {
+                if constexpr (kStream) __stcs(dst + (long long)j * p.ldc, out[j]);
+                else dst[(long long)j * p.ldc] = out[j];
+            }
     }
     if (p.H) {
         // shadow region: every row of the columns < h_cols, and the rows < h_rows of every column
@@ -88,15 +94,19 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.H) + row + (long long)col0 * p.ldh;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (!kRagged || (row < p.M && col0 + j < p.N && (row_in || col0 + j < p.h_cols)))
-                        dst[(long long)j * p.ldh] = __float2bfloat16_rn(out[j] * hs);
+                    if (!kRagged || (row < p.M && col0 + j < p.N && (row_in || col0 + j < p.h_cols))) {
+                        const __nv_bfloat16 hv = __float2bfloat16_rn(out[j] * hs);
+                        if constexpr (kStream) __stcs(reinterpret_cast<unsigned short*>(dst) + (long long)j * p.ldh, __bfloat16_as_ushort(hv));
+                        else dst[(long long)j * p.ldh] = hv;
+                    }
             } else {
                 __half* dst = reinterpret_cast<__half*>(p.H) + row + (long long)col0 * p.ldh;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float hv = out[j] * hs;
                     if (!kRagged || (row < p.M && col0 + j < p.N && (row_in || col0 + j < p.h_cols))) {
-                        dst[(long long)j * p.ldh] = __float2half_rn(hv);
+                        if constexpr (kStream) __stcs(reinterpret_cast<unsigned short*>(dst) + (long long)j * p.ldh, __half_as_ushort(__float2half_rn(hv)));
+                        else dst[(long long)j * p.ldh] = __float2half_rn(hv);
                         mx = fmaxf(mx, fabsf(hv));  // inf propagates; a NaN needs an inf operand, caught when it was made
                     }
                 }
@@ -105,7 +115,7 @@ __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (
     }
 }
 
-template <int kCG, bool kAMN, bool kRagged>
+template <int kCG, bool kAMN, bool kRagged, bool kStream = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
     // Up to kMaxGroup independent problems share one launch ("grouped"): tiles [tile_end[i-1], tile_end[i]) belong to
@@ -329,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
             }
             if (i < nchunks) {
                 if (lp->Cin != nullptr) {
-                    epi_load<kRagged>(cin_nxt, *lp, t_row0 + lane, nx_col0, nx_ok);
+                    epi_load<kRagged, kStream>(cin_nxt, *lp, t_row0 + lane, nx_col0, nx_ok);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) cin_nxt[j] = 0.f;
@@ -347,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                         else ptx::mbar_arrive_cluster(&tempty[as], 0);
                     }
                 }
-                epi_store<kRagged>(v, cin_cur, *cp, c_alpha, c_hs, cur_row0 + lane, cur_col0, cur_ok, mx);
+                epi_store<kRagged, kStream>(v, cin_cur, *cp, c_alpha, c_hs, cur_row0 + lane, cur_col0, cur_ok, mx);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) cin_cur[j] = cin_nxt[j];
@@ -381,10 +391,10 @@ EncodeFn get_encode_fn() {
     return fn;
 }
 
-template <int kCG, bool kAMN, bool kRagged>
+template <int kCG, bool kAMN, bool kRagged, bool kStream = false>
 int launch_variant(GemmGroup& g, int max_sms, cudaStream_t stream) {
     using C = Cfg<kCG>;
-    auto kern = gemm_tc_kernel<kCG, kAMN, kRagged>;
+    auto kern = gemm_tc_kernel<kCG, kAMN, kRagged, kStream>;
     long long tiles = 0;
     for (int i = 0; i < g.count; ++i) {
         tiles += (long long)((g.p[i].M + BM * kCG - 1) / (BM * kCG)) * ((g.p[i].N + BN - 1) / BN);
@@ -412,9 +422,9 @@ int launch_variant(GemmGroup& g, int max_sms, cudaStream_t stream) {
     return (int)cudaLaunchKernelEx(&cfg, kern, g);
 }
 
-template <int kCG, bool kAMN, bool kRagged>
+template <int kCG, bool kAMN, bool kRagged, bool kStream = false>
 int set_smem_attr() {
-    return (int)cudaFuncSetAttribute(gemm_tc_kernel<kCG, kAMN, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return (int)cudaFuncSetAttribute(gemm_tc_kernel<kCG, kAMN, kRagged, kStream>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      Cfg<kCG>::SMEM_BYTES);
 }
 
@@ -426,6 +436,8 @@ int gemm_tc_init() {
     if ((rc = set_smem_attr<2, true, false>())) return rc;
     if ((rc = set_smem_attr<1, false, false>())) return rc;
     if ((rc = set_smem_attr<2, false, false>())) return rc;
+    if ((rc = set_smem_attr<1, true, false, true>())) return rc;
+    if ((rc = set_smem_attr<2, true, false, true>())) return rc;
     if ((rc = set_smem_attr<1, true, true>())) return rc;
     if ((rc = set_smem_attr<2, true, true>())) return rc;
     if ((rc = set_smem_attr<1, false, true>())) return rc;
@@ -476,6 +488,10 @@ int launch_gemm_group(int variant, GemmGroup& g, int max_sms, cudaStream_t strea
     }
     // aligned fast path: whole 32 x 32 epilogue chunks (the factorization only ever issues these)
     if (!ragged) {
+        bool stream_c = true;  // only when every problem of the group asks for it
+        for (int i = 0; i < g.count; ++i) stream_c = stream_c && g.p[i].stream_c;
+        if (stream_c && variant == GEMM_CG1_AMN) return launch_variant<1, true, false, true>(g, max_sms, stream);
+        if (stream_c && variant == GEMM_CG2_AMN) return launch_variant<2, true, false, true>(g, max_sms, stream);
         switch (variant) {
             case GEMM_CG1_AMN: return launch_variant<1, true, false>(g, max_sms, stream);
             case GEMM_CG2_AMN: return launch_variant<2, true, false>(g, max_sms, stream);

@@ -41,6 +41,7 @@ struct GemmParams {
     int bf16;     // 0 = fp16 operands/shadow, 1 = bf16
     int* status;  // device word; bit 0 set when a shadow value overflowed the 16-bit range
     int pdl;      // 1 = launch with programmatic stream serialization (prologue overlaps the predecessor's tail)
+    int stream_c; // 1 = C / Cin / H are accessed with the streaming (evict-first) cache policy
     int tri;      // triangular operand: the K range of a tile is cut to the part where that operand is non-zero
                   // (TRI_NONE, TRI_A_LOWER: A(m,k)=0 for k>m, TRI_A_UPPER: k<m, TRI_B_UPPER: B(k,n)=0 for k>n, TRI_B_LOWER: k<n)
 };

@@ -15,6 +15,8 @@
 // No host<->device round trips inside the loop (the reference does one per panel, MPF.cu:146,158).
 #include "lu_internal.h"
 
+#include <vector>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -105,7 +107,10 @@ void resolve_options(mplu_context* c, int n) {
     if (c->opts.nb <= 0) c->opts.nb = n >= 12288 ? 2048 : (n >= 4096 ? 1024 : 512);
 }
 
-GemmParams gemm_params(const mplu_context* c, const GemmCall& g) {
+// programmatic dependent launch: everywhere (opts.pdl == 1) or on the chain lane only (opts.pdl == 2)
+inline int lane_pdl(const mplu_context* c, const Lane& ln) { return c->opts.pdl == 1 || (c->opts.pdl == 2 && ln.pdl); }
+
+GemmParams gemm_params(const mplu_context* c, const GemmCall& g, const Lane& ln) {
     GemmParams p{};
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.a_r0 = g.a_r0; p.a_c0 = g.a_c0; p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
@@ -117,8 +122,9 @@ GemmParams gemm_params(const mplu_context* c, const GemmCall& g) {
     p.hscale = 1.f; p.hscale_p = g.hscale_p;
     p.bf16 = c->opts.precision == MPLU_BF16;
     p.status = c->status;
-    p.pdl = c->opts.pdl;
+    p.pdl = lane_pdl(c, ln);
     p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
+    p.stream_c = (c->opts.stream_c && g.stream_c) ? 1 : 0;
     return p;
 }
 
@@ -141,7 +147,7 @@ int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
     const int variant = pick_variant(c, g);
     const bool cg2 = (variant == GEMM_CG2_AMN);
-    const GemmParams p = gemm_params(c, g);
+    const GemmParams p = gemm_params(c, g, ln);
     c->gemm_launches++;
     c->kernel_launches++;
     return launch_gemm_tc(variant, &g.A->mapA, cg2 ? &g.B->mapB2 : &g.B->mapB1, p, lane_sms(c, ln), ln.st);
@@ -158,7 +164,7 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
         return run_gemm(c, ln, g1);
     }
     const bool cg2 = (variant == GEMM_CG2_AMN);
-    const GemmParams p0 = gemm_params(c, g0), p1 = gemm_params(c, g1);
+    const GemmParams p0 = gemm_params(c, g0, ln), p1 = gemm_params(c, g1, ln);
     c->gemm_launches++;
     c->kernel_launches++;
     return launch_gemm_tc2(variant, &g0.A->mapA, cg2 ? &g0.B->mapB2 : &g0.B->mapB1, p0, &g1.A->mapA,
@@ -187,7 +193,7 @@ int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int c
         if (calls[i].M <= 0 || calls[i].N <= 0 || calls[i].K <= 0) continue;
         g.tmA[g.count] = calls[i].A->mapA;
         g.tmB[g.count] = cg2 ? calls[i].B->mapB2 : calls[i].B->mapB1;
-        g.p[g.count] = gemm_params(c, calls[i]);
+        g.p[g.count] = gemm_params(c, calls[i], ln);
         g.count++;
     }
     c->gemm_launches++;
@@ -211,8 +217,12 @@ struct Sched {
     // A[r0:r1, c0:c1) -= L[r0:r1, k0:k1) * U[k0:k1, c0:c1): operands from the factor shadow Fh, result in W and,
     // where asked, in the trailing shadow Wh (the reference's cublasDgemm, MPF.cu:230-239)
     GemmCall schur_call(int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
-        return GemmCall{&c->opFh, r0, k0, &c->opFh, k0, c0, r1 - r0, c1 - c0, k1 - k0, Wp(r0, c0), ld, true,
-                        Whp(r0, c0), ld, h_rows, h_cols, 1.f, sc(SC_NEG_LA_INV), nullptr, sc(SC_A)};
+        GemmCall g{&c->opFh, r0, k0, &c->opFh, k0, c0, r1 - r0, c1 - c0, k1 - k0, Wp(r0, c0), ld, true,
+                   Whp(r0, c0), ld, h_rows, h_cols, 1.f, sc(SC_NEG_LA_INV), nullptr, sc(SC_A)};
+        // updates much larger than a diagonal tile: their C / shadow traffic is touched once per launch and exceeds L2,
+        // so it goes through the streaming cache policy (the tile-sized updates of the chain lane stay cacheable)
+        g.stream_c = (long long)(r1 - r0) * (c1 - c0) >= (8ll << 20);
+        return g;
     }
     int schur(const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
         return run_gemm(c, ln, schur_call(r0, r1, c0, c1, k0, k1, h_rows, h_cols));
@@ -244,7 +254,7 @@ struct Sched {
             uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
             uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
             CKI(launch_diag_lu(c->W, ld, c0, l16, u16, ldi, c->Linv32, c->Uinv32, ts(T), c0 == T, blk,
-                               c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, c->opts.pdl,
+                               c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, lane_pdl(c, ln),
                                c->n - c0 < kDiagBlock ? c->n - c0 : kDiagBlock));
             c->kernel_launches++;
             return 0;
@@ -381,7 +391,7 @@ int enqueue_factorization(mplu_context* c) {
     const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && npad > 2 * NB;
     const Lane all{st, 0};
     Lane bulk = two ? Lane{st, c->num_sms - side_sms} : all;
-    Lane chain = two ? Lane{c->side, side_sms} : all;
+    Lane chain = two ? Lane{c->side, side_sms, true} : all;
     // While the trailing matrix is large the schedule is bound by the bulk lane (the chain lane waits for it), so the
     // chain gets fewer SMs there: side_sms_early while more than early_frac of the columns remain.
     int side_early = c->opts.side_sms_early > 0 ? c->opts.side_sms_early : side_sms;
@@ -485,6 +495,173 @@ int enqueue_factorization(mplu_context* c) {
     return 0;
 }
 
+// opts.schedule == MPLU_SCHED_LEFT: left-looking by nb-wide block columns with look-ahead.
+// The right-looking schedule above front-loads the tensor-core work (step k updates the whole trailing matrix), so its
+// first steps are bound by the bulk lane and its last ~10 by the latency-bound GETRF chain with the bulk lane idle.
+// Left-looking, block column j receives all of its updates k < j just before its turn; the amount of update work per
+// step GROWS with j instead of shrinking, and every step has less of it than one GETRF takes: the chain lane never
+// waits for more than the two-tile update it does itself, and the bulk lane's rank-nb updates (tall (n - k nb) x nb
+// products, the best-shaped GEMMs of the factorization) hide behind the chain.  Per tile the same products are
+// formed in the same order: the factors are bit-identical to the right-looking schedule's.
+//   chain, step j:  U(j-1,j) = inv(L(j-1,j-1)) A(j-1,j);  tile (j,j) -= L(j,j-1) U(j-1,j);  GETRF(D_j);
+//                   L(j+1,j) = A(j+1,j) inv(U(j,j))
+//   bulk,  step j:  rows below tile j of column j -= L(.,j-1) U(j-1,j);   column j+1: updates k = 0..j-1;
+//                   L(j+2:,j) = A(j+2:,j) inv(U(j,j))
+int enqueue_factorization_left(mplu_context* c) {
+    const int npad = c->npad;
+    const long long ld = npad;
+    const int bf16 = c->opts.precision == MPLU_BF16;
+    const int NB = effective_nb(c, npad);
+    const int nt = (npad + NB - 1) / NB;
+    if (nt >= mplu_context::kMaxSteps) return MPLU_E_ARG;
+    cudaStream_t st = c->stream;
+    int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 32;
+    side_sms -= side_sms % 2;
+    const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && nt > 2;
+    const Lane all{st, 0};
+    const Lane bulk = two ? Lane{st, c->num_sms - side_sms} : all;
+    const Lane chain = two ? Lane{c->side, side_sms, true} : all;
+    const Sched S{c, ld, (long long)c->cap_nb};
+    // chain: U(j-1,j) ready, GETRF(D_j) done; bulk: column j has its updates k < j-1, rows below tile j of column j have update j-1
+    enum { EV_U = 0, EV_G = 1, EV_COL = 2, EV_B1 = 3 };
+    cudaEvent_t ev = nullptr;
+
+    CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+    if (npad > NB)
+        CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
+                               c->scales + SC_A, bf16, c->status, st));
+    c->kernel_launches += 3;
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+
+    CKI(S.getrf(all, 0, 0, NB));
+    if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
+    if (two) {
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    }
+    // the bulk lane's tall updates: rows r0.. of block columns [c0, c1), full shadow
+    // `last`: this is the block columns' final update (k = column - 1): everything below gets its 16-bit shadow (the
+    // GETRF / L-panel solve read it); an intermediate update only shadows tile row k+1, which the next panel solve
+    // U(k+1,.) reads -- the rest would be overwritten by update k+1 anyway, and the full-shadow epilogue costs the
+    // tall update a fifth of its rate (855 vs 1109 TFLOP/s at 30720 x 30720 x 2048)
+    auto big_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1, bool last) -> int {
+        return S.schur(ln, r0, npad, c0, c1, k0, k1, last ? npad - r0 : NB, last ? c1 - c0 : 0);
+    };
+    auto timed_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1) -> int {
+        // every rank-nb update of the bulk lane is timed with its own event pair for the roofline figure
+        const bool timed = c->trail_count < mplu_context::kMaxTrail;
+        if (timed) {
+            cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
+            if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
+            CKI(record_event(c, e0, ln.st));
+        }
+        CKI(big_schur(ln, r0, c0, c1, k0, k1, false));
+        if (timed) {
+            CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], ln.st));
+            c->trail_count++;
+            c->trail_flops += 2.0 * (npad - r0) * (double)(c1 - c0) * (k1 - k0);
+            c->trail_bytes += 8.0 * (npad - r0) * (double)(c1 - c0);
+        }
+        return 0;
+    };
+    // bulk-lane bookkeeping: done[m] = number of updates (k < done[m]) block column m has received below tile row k
+    std::vector<int> done(nt, 0);
+    auto colb = [&](int m) { return m * NB < npad ? m * NB : npad; };
+    auto cost = [&](int k, int m0, int m1) {  // flops of update k on block columns [m0, m1): panel solve + Schur update
+        const double N = colb(m1) - colb(m0);
+        return 2.0 * (npad - (k + 1) * NB) * N * NB + (double)NB * NB * N;
+    };
+    auto apply = [&](int k, int m0, int m1) -> int {
+        const int k0 = k * NB, k1 = k0 + NB, d0 = colb(m0), d1 = colb(m1);
+        CKI(S.trsm_u(bulk, k0, k0, NB, d0, d1));
+        return timed_schur(bulk, k1, d0, d1, k0, k1);
+    };
+    double remaining = 0.0;  // update work the bulk lane still has to place: updates k <= m-2 of every column m >= 2
+    for (int m = 2; m < nt; ++m)
+        for (int k = 0; k + 2 <= m; ++k) remaining += cost(k, m, m + 1);
+    for (int j = 1; j < nt; ++j) {
+        const int c0 = j * NB, c1 = (c0 + NB < npad) ? c0 + NB : npad, w = c1 - c0;
+        const int c2 = (c1 + NB < npad) ? c1 + NB : npad;  // end of tile row j+1
+        const int kp = c0 - NB;                             // previous block column [kp, c0)
+        // ---- chain lane
+        if (two && j >= 2) {  // the bulk lane gave column j its updates k < j-1
+            CKI(step_event(c, j, EV_COL, &ev));
+            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+        }
+        if (!two)  // single lane: plain left-looking, column j receives its updates k < j-1 here
+            for (int k = 0; k + 2 <= j; ++k) CKI(apply(k, j, j + 1));
+        CKI(mark(c, 1000 + j, chain.st));
+        CKI(S.trsm_u(chain, kp, kp, NB, c0, c1));
+        if (two) { CKI(step_event(c, j, EV_U, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        CKI(S.schur(chain, c0, two ? c1 : npad, c0, c1, kp, c0, (two ? c1 : npad) - c0, w));
+        CKI(mark(c, 2000 + j, chain.st));
+        CKI(S.getrf(chain, c0, c0, w));
+        CKI(mark(c, 3000 + j, chain.st));
+        if (two) { CKI(step_event(c, j, EV_G, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (!two) {
+            if (c1 < npad) CKI(S.trsm_l(chain, c0, c0, w, c1, npad));
+            continue;
+        }
+        // ---- bulk lane
+        CKI(step_event(c, j, EV_U, &ev));
+        CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+        CKI(mark(c, 4000 + j, bulk.st));
+        if (c1 < npad) {
+            CKI(big_schur(bulk, c1, c0, c1, kp, c0, true));
+            CKI(step_event(c, j, EV_B1, &ev));
+            CK(cudaEventRecord(ev, bulk.st));
+        }
+        CKI(mark(c, 5000 + j, bulk.st));
+        if (j + 1 < nt) {
+            // mandatory: block column j+1 receives every update k < j it has not seen yet
+            double spent = 0.0;
+            for (int k = done[j + 1]; k < j; ++k) { CKI(apply(k, j + 1, j + 2)); spent += cost(k, j + 1, j + 2); }
+            done[j + 1] = j;
+            CKI(step_event(c, j + 1, EV_COL, &ev));
+            CK(cudaEventRecord(ev, bulk.st));
+            // eager: spend the rest of this step's share of the remaining update work on the columns behind it, nearest
+            // first, a run of equally advanced columns per launch (this is what balances the lanes: left-looking alone
+            // leaves the bulk lane idle in the first steps and overloads it in the last ones)
+            const double share = c->opts.eager ? remaining / (double)(nt - 1 - j) : 0.0;
+            while (spent < share) {
+                int m = j + 2;
+                while (m < nt && done[m] >= j) ++m;
+                if (m >= nt) break;
+                const int d = done[m];
+                int m1 = m + 1;
+                while (m1 < nt && done[m1] == d) ++m1;
+                const int fit = (int)((share - spent) / cost(d, m, m + 1) + 0.5);
+                if (m1 - m > fit) m1 = m + (fit > 1 ? fit : 1);
+                CKI(apply(d, m, m1));
+                spent += cost(d, m, m1);
+                for (int i = m; i < m1; ++i) done[i] = d + 1;
+            }
+            remaining -= spent;
+        }
+        CKI(mark(c, 6000 + j, bulk.st));
+        if (c2 < npad) {
+            CKI(step_event(c, j, EV_G, &ev));
+            CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+            CKI(S.trsm_l(bulk, c0, c0, w, c2, npad));
+        }
+        CKI(mark(c, 7000 + j, bulk.st));
+        // ---- chain lane again (issued after the bulk lane's record of EV_B1: a wait must follow its record in host
+        // order to be captured): tile j+1 of column j has received update j-1 from the bulk lane long before
+        if (c1 < npad) {
+            CKI(step_event(c, j, EV_B1, &ev));
+            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(S.trsm_l(chain, c0, c0, w, c1, c2));
+        }
+    }
+    if (two) {
+        CK(cudaEventRecord(c->ev_join, c->side));
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
+    return 0;
+}
+
 int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     CKI(ensure_work(c, n));
     const int npad = c->npad;
@@ -503,7 +680,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
                                c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8) + (c->opts.tri_skip << 1),
-                               c->W, c->tile ? (const void*)c->tile->W : nullptr};
+                               c->W, c->tile ? (const void*)c->tile->W : nullptr, c->opts.schedule + 2 * c->opts.eager + 4 * c->opts.stream_c + 8 * c->opts.side_sms_left};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
         c->gemm_launches = 0;
@@ -515,7 +692,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
             if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
             c->capturing = true;
-            int rc = enqueue_factorization(c);
+            int rc = c->opts.schedule == MPLU_SCHED_LEFT ? enqueue_factorization_left(c) : enqueue_factorization(c);
             c->capturing = false;
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -529,7 +706,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
             c->g_gemm_launches = c->gemm_launches; c->g_kernel_launches = c->kernel_launches;
             c->g_trail_count = c->trail_count; c->g_trail_flops = c->trail_flops; c->g_trail_bytes = c->trail_bytes;
         } else {
-            CKI(enqueue_factorization(c));
+            CKI(c->opts.schedule == MPLU_SCHED_LEFT ? enqueue_factorization_left(c) : enqueue_factorization(c));
         }
     }
     if (use_graph) {
@@ -598,7 +775,9 @@ int factor_streamed(mplu_context* c, int n, const double* hA, long long lda, dou
         for (int k0 = 0; k0 < c0; k0 += NB) {
             const int k1 = k0 + NB;
             CKI(S.trsm_u(all, k0, k0, NB, c0, c1));
-            CKI(S.schur(all, k1, npad, c0, c1, k0, k1, npad - k1, w));
+            // the last update shadows everything below (GETRF / L-panel solve read it), the others only tile row k+1
+            const bool last = k1 >= c0;
+            CKI(S.schur(all, k1, npad, c0, c1, k0, k1, last ? npad - k1 : NB, last ? w : 0));
         }
         CKI(S.getrf(all, c0, c0, w));
         if (c1 < npad) CKI(S.trsm_l(all, c0, c0, w, c1, npad));
@@ -730,6 +909,10 @@ void mplu_default_options(mplu_options* o) {
     o->late_pct = 35;
     o->tri_skip = 1;
     o->stream_host = 1;
+    o->schedule = MPLU_SCHED_LEFT;
+    o->side_sms_left = 32;
+    o->eager = 1;
+    o->stream_c = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {

@@ -62,7 +62,7 @@ struct mplu_context {
     static constexpr int kMaxSteps = 512;
     cudaEvent_t ev_step[4 * kMaxSteps] = {};  // per step: GETRF done, next-tile TRSM done, b2 done, b3a done
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group, tile_ws; const void* W; const void* TW; } gkey{};
+    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group, tile_ws; const void* W; const void* TW; int schedule; } gkey{};
     int g_gemm_launches = 0, g_kernel_launches = 0, g_trail_count = 0;
     double g_trail_flops = 0, g_trail_bytes = 0;
     bool capturing = false;
@@ -108,12 +108,14 @@ struct GemmCall {
     const float* alpha_p2;
     const float* hscale_p;               // H = cvt16(out * *hscale_p)
     int tri = 0;                         // GemmTri: which operand is triangular (its zero part of K is skipped)
+    bool stream_c = false;               // C / H are far larger than L2 and touched once: streaming cache policy
 };
 
 // Where a piece of the schedule runs: stream + SM budget (0 = all SMs).
 struct Lane {
     cudaStream_t st;
     int sms;
+    bool pdl = false;  // chain lane: opts.pdl == 2 launches its kernels programmatically
 };
 
 

@@ -278,8 +278,9 @@ def test_fp16_overflow_falls_back_to_bf16(mplu, oracle, solver):
 
 
 def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
-    """Grouped launches, triangular K-range skipping, lane split, CUDA graph, workspace GETRF only change WHEN and WHERE
-    the same products are formed: the factors are bit-identical."""
+    """Grouped launches, triangular K-range skipping, lane split, CUDA graph, workspace GETRF, the left-looking schedule
+    (schedule=1) and chain-lane programmatic launches only change WHEN and WHERE the same products are formed: the
+    factors are bit-identical."""
     import torch
     n = 2304  # not a multiple of the tile size: the last tile is partial
     A = oracle.counter_matrix(n, seed=4)
@@ -288,8 +289,13 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
     ref = None
     s = mplu.Solver(0)
     try:
-        for kw in (dict(), dict(group=0), dict(tri_skip=0), dict(lookahead=0), dict(use_graph=0), dict(tile_ws=1),
-                   dict(side_sms=16, side_sms_early=8), dict(gemm_variant=mplu.GEMM_CG2)):
+        common = (dict(), dict(group=0), dict(tri_skip=0), dict(lookahead=0), dict(use_graph=0), dict(gemm_variant=mplu.GEMM_CG2),
+                  dict(stream_c=0))
+        right = tuple(dict(schedule=0, **kw) for kw in common) + (
+            dict(schedule=0, tile_ws=1), dict(schedule=0, side_sms=16, side_sms_early=8), dict(schedule=0, pdl=2))
+        left = tuple(dict(schedule=1, **kw) for kw in common) + (
+            dict(schedule=1, eager=0), dict(schedule=1, use_graph=0, side_sms_left=64), dict(schedule=1, side_sms_left=16))
+        for kw in right + left:
             x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
             LU = s.factors(n)
             assert st.converged == 1
