@@ -393,6 +393,9 @@ def main():
         del hA
 
     if rank == 0:
+        num_sms = torch.cuda.get_device_properties(local).multi_processor_count
+        left = int(opts.schedule) == 1
+        bulk_sms = num_sms - (int(opts.side_sms_left) if left else int(opts.side_sms))
         value = world * flops(n) / (ms_max * 1e-3) / 1e12
         ach = (tr_fl / (tr_ms * 1e-3) / 1e12) if tr_ms > 0 else None
         line = dict(metric=METRIC, value=value, unit="TFLOP/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -401,15 +404,22 @@ def main():
                     config=dict(workload=f"n={n} mixed-precision LU+IR on 1 B200 per rank (BASELINE.json configs[2])" if n == 32768
                                 else f"n={n} mixed-precision LU+IR", n=n,
                                 nb=int(opts.nb) or (2048 if n >= 12288 else (1024 if n >= 4096 else 512)), rhs=1,
+                                schedule="left-looking block columns, look-ahead + eager updates" if int(opts.schedule) == 1
+                                else "right-looking, depth-1 look-ahead",
+                                host_path="streamed by block columns behind the H2D copy" if int(opts.stream_host) else "copy, then solve",
                                 matrix="column-diagonally-dominant, values k/10 (reference generator distribution), seed=1+rank",
                                 l2_policy="inputs larger than L2 (A is %.1f GiB)" % (8.0 * n * n / 2 ** 30),
                                 parallelism=("replicas x%d" % world) if world > 1 else "single GPU"),
                     ir_iters=iters, backward_error=worst_be, max_abs_err=fwd_err,
                     factor_ms=st.factor_ms, solve_ms=st.solve_ms,
                     gpu_launches=launches, clocks=clocks, e2e=e2e,
-                    roofline=dict(bound="tensor", kernel="gemm_tc_kernel (rank-nb trailing update)", achieved=ach,
+                    roofline=dict(bound="tensor", kernel="gemm_tc_kernel (rank-nb Schur updates of the bulk lane)", achieved=ach,
                                   peak=pk["tc_sustained"], unit="TFLOP/s", frac=(ach / pk["tc_sustained"]) if ach else None,
                                   peak_kind=f"bf16_tflops_sustained ({pk['src']}); burst {pk['tc_burst']}",
+                                  # these launches run on the bulk lane's SM budget while the chain lane factors the next
+                                  # diagonal tile on the other SMs: frac is against the WHOLE GPU's peak
+                                  sms=bulk_sms, sms_total=num_sms,
+                                  frac_of_lane_peak=(ach / (pk["tc_sustained"] * bulk_sms / num_sms)) if ach else None,
                                   launches=tr_n, avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
                                   share_of_step=(tr_ms / args.steps / ms) if ms > 0 else None,
                                   algorithmic_c_bytes_per_s=(tr_by / (tr_ms * 1e-3) / 1e9) if tr_ms > 0 else None,

@@ -201,6 +201,8 @@ int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int c
     return launch_gemm_group(variant, g, lane_sms(c, ln), ln.st);
 }
 
+int mark(mplu_context* c, int tag, cudaStream_t st);
+
 inline int split_width(int w) { return kDiagBlock * ((w / kDiagBlock + 1) / 2); }
 
 struct Sched {
@@ -253,11 +255,12 @@ struct Sched {
             const int blk = c0 / kDiagBlock;
             uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
             uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
+            CKI(mark(c, 8000 + blk, ln.st));  // development aid (mplu_debug_marks_enable): leaf start / end
             CKI(launch_diag_lu(c->W, ld, c0, l16, u16, ldi, c->Linv32, c->Uinv32, ts(T), c0 == T, blk,
                                c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, lane_pdl(c, ln),
                                c->n - c0 < kDiagBlock ? c->n - c0 : kDiagBlock));
             c->kernel_launches++;
-            return 0;
+            return mark(c, 9000 + blk, ln.st);
         }
         const int h = split_width(w), g = w - h, c1 = c0 + h;
         CKI(getrf(ln, T, c0, h));
