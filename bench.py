@@ -30,8 +30,8 @@ def flops(n):
 
 
 def measured_traffic():
-    """DRAM bytes of one rank-2048 trailing-update launch from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "traffic_gemm_trailing.json")
+    """DRAM bytes of one rank-2048 update launch of the bulk lane from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic_gemm_update.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))

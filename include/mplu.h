@@ -76,6 +76,9 @@ typedef struct mplu_options {
                          schedule's) */
     int stream_c;     /* 1 (default): the tall rank-nb updates load / store their fp32 C and 16-bit shadow with the streaming
                          (evict-first) cache policy: that traffic is touched once per launch and far larger than L2 */
+    int early_scale;  /* MPLU_SCHED_LEFT, mplu_gesv_device: 1 (default) = the first touch of A overlaps the first diagonal
+                         tile's GETRF; the fp16 scale then comes from the first block column and a later overflow is
+                         redone with the global scale; 0 = global scale from a full first pass */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -529,17 +529,18 @@ int enqueue_factorization_left(mplu_context* c) {
     enum { EV_U = 0, EV_G = 1, EV_COL = 2, EV_B1 = 3 };
     cudaEvent_t ev = nullptr;
 
-    CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
-    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
-    if (npad > NB)
-        CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
-                               c->scales + SC_A, bf16, c->status, st));
-    c->kernel_launches += 3;
-    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
-    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
-
-    CKI(S.getrf(all, 0, 0, NB));
-    if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
+    if (!c->prologue_done) {  // else prologue_left() has done this part, overlapped with the first touch
+        CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+        CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+        if (npad > NB)
+            CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
+                                   c->scales + SC_A, bf16, c->status, st));
+        c->kernel_launches += 3;
+        CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+        CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+        CKI(S.getrf(all, 0, 0, NB));
+        if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
+    }
     if (two) {
         CK(cudaEventRecord(c->ev_fork, st));
         CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
@@ -665,12 +666,66 @@ int enqueue_factorization_left(mplu_context* c) {
     return 0;
 }
 
+// Left-looking schedule, first block column: the first touch of A (12 n^2 bytes, HBM bound, 2 ms at n = 32768) and the
+// GETRF of the first diagonal tile (latency bound, 1.3 ms, 2-40 SMs) overlap instead of running back to back.  The
+// first block column is cast first; the fp16 scale is fixed from ITS largest magnitude (it holds the first diagonal
+// tile; bf16 has no scale); then the second stream factors tile 0 and solves the first L panel while this stream casts
+// the other block columns.  A later block column that leaves the fp16 range under that scale raises the overflow bit
+// and mplu_gesv_device redoes the factorization with the global scale (opts.early_scale = 0 asks for that directly).
+// Direct launches, not part of the captured graph: they carry the caller's A pointer.
+int prologue_left(mplu_context* c, const double* dA, long long lda) {
+    const int n = c->n, npad = c->npad;
+    const long long ld = npad;
+    const int bf16 = c->opts.precision == MPLU_BF16;
+    const int NB = effective_nb(c, npad);
+    const int nt = (npad + NB - 1) / NB;
+    cudaStream_t st = c->stream;
+    const int s0 = c->nchunk / nt > 0 ? c->nchunk / nt : 1;  // row-sum slots of the first block column
+    if (!c->ev_pro[0]) { CK(cudaEventCreateWithFlags(&c->ev_pro[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_pro[1], cudaEventDisableTiming)); }
+    CK(cudaMemsetAsync(c->amax, 0, sizeof(float), st));
+    CKI(launch_first_touch_cols(dA, lda, n, c->W, ld, npad, 0, NB, c->amax, c->rowsum_part, 0, s0, st));
+    CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    c->kernel_launches += 3;
+    CK(cudaEventRecord(c->ev_pro[0], st));
+    CK(cudaStreamWaitEvent(c->side, c->ev_pro[0], 0));
+    {   // second stream: tile 0 and the first L panel, every SM it can get next to the bandwidth-bound cast
+        const Sched S{c, ld, (long long)c->cap_nb};
+        const Lane lane{c->side, 0};
+        CKI(S.getrf(lane, 0, 0, NB));
+        CKI(S.trsm_l(lane, 0, 0, NB, NB, npad));
+        CK(cudaEventRecord(c->ev_pro[1], c->side));
+    }
+    CKI(launch_first_touch_cols(dA, lda, n, c->W, ld, npad, NB, npad, c->amax, c->rowsum_part, s0, c->nchunk - s0, st));
+    CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB, c->scales + SC_A,
+                           bf16, c->status, st));
+    CKI(launch_anorm(c->rowsum_part, n, c->nchunk, c->anorm, st));
+    c->kernel_launches += 3;
+    CK(cudaStreamWaitEvent(st, c->ev_pro[1], 0));
+    return 0;
+}
+
 int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     CKI(ensure_work(c, n));
     const int npad = c->npad;
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
-    CKI(launch_first_touch(dA, lda, n, c->W, npad, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
+    // left-looking schedule with at least two block columns: the first touch overlaps the first diagonal tile
+    const bool early = c->opts.schedule == MPLU_SCHED_LEFT && c->opts.early_scale != 0 && c->allow_early &&
+                       npad > effective_nb(c, npad) && c->opts.tile_ws == 0;
+    c->prologue_done = early;
+    c->used_early_scale = early && c->opts.precision != MPLU_BF16;
+    int pro_gemm = 0, pro_kern = 0;
+    if (early) {
+        c->gemm_launches = c->kernel_launches = 0;
+        CKI(prologue_left(c, dA, lda));
+        pro_gemm = c->gemm_launches;
+        pro_kern = c->kernel_launches;
+    } else {
+        CKI(launch_first_touch(dA, lda, n, c->W, npad, npad, c->amax, c->rowsum_part, c->nchunk, c->anorm, st));
+    }
 
     const bool use_graph = c->opts.use_graph != 0;
     {
@@ -683,11 +738,11 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
                                c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
                                c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8) + (c->opts.tri_skip << 1),
-                               c->W, c->tile ? (const void*)c->tile->W : nullptr, c->opts.schedule + 2 * c->opts.eager + 4 * c->opts.stream_c + 8 * c->opts.side_sms_left};
+                               c->W, c->tile ? (const void*)c->tile->W : nullptr, c->opts.schedule + 2 * c->opts.eager + 4 * c->opts.stream_c + 8 * (int)early + 16 * c->opts.side_sms_left};
     const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
     if (!hit) {
         c->gemm_launches = 0;
-        c->kernel_launches = 2;  // first touch + anorm
+        c->kernel_launches = early ? 0 : 2;  // first touch + anorm
         c->trail_count = 0;
         c->trail_flops = c->trail_bytes = 0;
         c->mark_count = 0;
@@ -717,6 +772,8 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
         c->trail_count = c->g_trail_count; c->trail_flops = c->g_trail_flops; c->trail_bytes = c->g_trail_bytes;
         CK(cudaGraphLaunch(c->graph_exec, st));
     }
+    c->gemm_launches += pro_gemm;
+    c->kernel_launches += pro_kern;
     c->factored = true;
     return 0;
 }
@@ -916,6 +973,7 @@ void mplu_default_options(mplu_options* o) {
     o->side_sms_left = 32;
     o->eager = 1;
     o->stream_c = 1;
+    o->early_scale = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -961,6 +1019,7 @@ void mplu_destroy(mplu_context* c) {
     for (auto& e : c->ev_step) if (e) cudaEventDestroy(e);
     for (auto& e : c->mark_ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_copy) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_pro) if (e) cudaEventDestroy(e);
     if (c->copy) cudaStreamDestroy(c->copy);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -978,7 +1037,10 @@ int mplu_factor_device(mplu_context* c, int n, const double* dA, long long lda, 
     if (opts) c->opts = *opts;
     resolve_options(c, n);
     c->factored = false;
-    return factor_impl(c, n, dA, lda);
+    c->allow_early = false;  // factor and solve are separate calls here: nothing could redo an early-scale overflow
+    const int rc = factor_impl(c, n, dA, lda);
+    c->allow_early = true;
+    return rc;
 }
 
 int mplu_solve_device(mplu_context* c, const double* dA, long long lda, const double* db, double* dx,
@@ -1002,6 +1064,16 @@ int mplu_gesv_device(mplu_context* c, int n, const double* dA, long long lda, co
     if (rc) return rc;
     CK(cudaEventRecord(c->ev[1], c->stream));
     rc = solve_impl(c, dA, lda, db, dx, stats);
+    if (rc == MPLU_E_OVERFLOW && c->used_early_scale) {
+        // the fp16 scale taken from the first block column did not fit a later one: once more with the global scale
+        c->allow_early = false;
+        c->factored = false;
+        rc = factor_impl(c, n, dA, lda);
+        c->allow_early = true;
+        if (rc) return rc;
+        if (stats) memset(stats, 0, sizeof(*stats));
+        rc = solve_impl(c, dA, lda, db, dx, stats);
+    }
     if (rc == MPLU_E_OVERFLOW && c->opts.precision == MPLU_FP16 && c->opts.bf16_fallback) {
         // like dsgesv's fall back to full precision: same algorithm, operand type without the range problem
         c->opts.precision = MPLU_BF16;

@@ -49,6 +49,9 @@ struct mplu_context {
     cudaStream_t copy = nullptr;
     cudaEvent_t ev_copy[512] = {};
     int copy_last = 0;
+    // left-looking prologue (first touch overlapped with the first diagonal tile)
+    cudaEvent_t ev_pro[2] = {nullptr, nullptr};
+    bool prologue_done = false, used_early_scale = false, allow_early = true;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {
         uint16_t* base = nullptr;
