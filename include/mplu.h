@@ -76,9 +76,11 @@ typedef struct mplu_options {
                          schedule's) */
     int stream_c;     /* 1 (default): the tall rank-nb updates load / store their fp32 C and 16-bit shadow with the streaming
                          (evict-first) cache policy: that traffic is touched once per launch and far larger than L2 */
-    int early_scale;  /* MPLU_SCHED_LEFT, mplu_gesv_device: 1 (default) = the first touch of A overlaps the first diagonal
-                         tile's GETRF; the fp16 scale then comes from the first block column and a later overflow is
-                         redone with the global scale; 0 = global scale from a full first pass */
+    int early_scale;  /* MPLU_SCHED_LEFT, mplu_gesv_device: 1 = the first touch of A overlaps the first diagonal tile's
+                         GETRF; the fp16 scale then comes from the first block column and an overflow that spoils the
+                         solve is redone with the global scale.  Default 0: measured neutral (35.5 vs 35.9 ms and 37.1
+                         vs 37.0 ms on two boxes) -- the bandwidth-bound cast slows the latency-bound tile as much as
+                         the overlap saves */
 } mplu_options;
 
 typedef struct mplu_stats {
@@ -107,6 +109,9 @@ typedef struct mplu_stats {
 } mplu_stats;
 
 void mplu_default_options(mplu_options *opts);
+/* sizeof(mplu_options) / sizeof(mplu_stats) of the library, for bindings that mirror the structs */
+int mplu_sizeof_options(void);
+int mplu_sizeof_stats(void);
 
 int mplu_create(mplu_context **ctx, int device);
 void mplu_destroy(mplu_context *ctx);
@@ -146,6 +151,11 @@ int mplu_gemm16(int variant, int bf16, int M, int N, int K, float alpha, const v
 
 /* No-pivot LU of one 128x128 fp32 block in place + explicit inverses (fp32, column-major 128x128 each). */
 int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *stream);
+
+/* Host logic of the left-looking schedule (no device needed): the bulk lane's update plan for an n x n matrix tiled
+ * by nb as (step, k, m0, m1, mandatory) quintuples -- update k applied to block columns [m0, m1) during step `step`.
+ * Returns the number of ops; at most `max` are written to out[0 .. 5*max). */
+int mplu_debug_plan_left(int n, int nb, int eager, int *out, int max);
 
 /* r = b - A x in fp64; norms[0] = ||r||_inf, norms[1] = ||x||_inf (device array of 2 doubles). */
 int mplu_residual(int n, const double *dA, long long lda, const double *dx, const double *db, double *dr,

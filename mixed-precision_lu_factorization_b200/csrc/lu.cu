@@ -498,6 +498,51 @@ int enqueue_factorization(mplu_context* c) {
     return 0;
 }
 
+// Bulk-lane plan of the left-looking schedule (pure host logic; mplu_debug_plan_left exposes it to the CPU tests).
+// Block column m (m >= 2) must receive the updates k = 0 .. m-2 in increasing k before step m, and update k can only be
+// applied from step k+1 on (its L panel is complete then).  Step j first brings block column j+1 up to date
+// (mandatory), then spends the rest of its share of the remaining update flops on the columns further right, nearest
+// first, one op per run of equally advanced columns.  An op applies update k to block columns [m0, m1).
+struct LeftOp { int step, k, m0, m1, mandatory; };
+
+std::vector<LeftOp> plan_left(int npad, int NB, bool eager) {
+    const int nt = (npad + NB - 1) / NB;
+    std::vector<LeftOp> ops;
+    std::vector<int> done(nt > 0 ? nt : 1, 0);  // done[m]: block column m has received the updates k < done[m]
+    auto colb = [&](int m) { return (long long)m * NB < npad ? m * NB : npad; };
+    auto cost = [&](int k, int m0, int m1) {  // flops of update k on block columns [m0, m1): panel solve + Schur update
+        const double N = colb(m1) - colb(m0);
+        return 2.0 * (npad - (k + 1) * NB) * N * NB + (double)NB * NB * N;
+    };
+    double remaining = 0.0;
+    for (int m = 2; m < nt; ++m)
+        for (int k = 0; k + 2 <= m; ++k) remaining += cost(k, m, m + 1);
+    for (int j = 1; j + 1 < nt; ++j) {
+        double spent = 0.0;
+        for (int k = done[j + 1]; k < j; ++k) {
+            ops.push_back({j, k, j + 1, j + 2, 1});
+            spent += cost(k, j + 1, j + 2);
+        }
+        done[j + 1] = j;
+        const double share = eager ? remaining / (double)(nt - 1 - j) : 0.0;
+        while (spent < share) {
+            int m = j + 2;
+            while (m < nt && done[m] >= j) ++m;
+            if (m >= nt) break;
+            const int d = done[m];
+            int m1 = m + 1;
+            while (m1 < nt && done[m1] == d) ++m1;
+            const int fit = (int)((share - spent) / cost(d, m, m + 1) + 0.5);
+            if (m1 - m > fit) m1 = m + (fit > 1 ? fit : 1);
+            ops.push_back({j, d, m, m1, 0});
+            spent += cost(d, m, m1);
+            for (int i = m; i < m1; ++i) done[i] = d + 1;
+        }
+        remaining -= spent;
+    }
+    return ops;
+}
+
 // opts.schedule == MPLU_SCHED_LEFT: left-looking by nb-wide block columns with look-ahead.
 // The right-looking schedule above front-loads the tensor-core work (step k updates the whole trailing matrix), so its
 // first steps are bound by the bulk lane and its last ~10 by the latency-bound GETRF chain with the bulk lane idle.
@@ -570,21 +615,14 @@ int enqueue_factorization_left(mplu_context* c) {
         }
         return 0;
     };
-    // bulk-lane bookkeeping: done[m] = number of updates (k < done[m]) block column m has received below tile row k
-    std::vector<int> done(nt, 0);
     auto colb = [&](int m) { return m * NB < npad ? m * NB : npad; };
-    auto cost = [&](int k, int m0, int m1) {  // flops of update k on block columns [m0, m1): panel solve + Schur update
-        const double N = colb(m1) - colb(m0);
-        return 2.0 * (npad - (k + 1) * NB) * N * NB + (double)NB * NB * N;
-    };
     auto apply = [&](int k, int m0, int m1) -> int {
         const int k0 = k * NB, k1 = k0 + NB, d0 = colb(m0), d1 = colb(m1);
         CKI(S.trsm_u(bulk, k0, k0, NB, d0, d1));
         return timed_schur(bulk, k1, d0, d1, k0, k1);
     };
-    double remaining = 0.0;  // update work the bulk lane still has to place: updates k <= m-2 of every column m >= 2
-    for (int m = 2; m < nt; ++m)
-        for (int k = 0; k + 2 <= m; ++k) remaining += cost(k, m, m + 1);
+    const std::vector<LeftOp> plan = plan_left(npad, NB, c->opts.eager != 0);
+    size_t pi = 0;
     for (int j = 1; j < nt; ++j) {
         const int c0 = j * NB, c1 = (c0 + NB < npad) ? c0 + NB : npad, w = c1 - c0;
         const int c2 = (c1 + NB < npad) ? c1 + NB : npad;  // end of tile row j+1
@@ -619,30 +657,13 @@ int enqueue_factorization_left(mplu_context* c) {
         }
         CKI(mark(c, 5000 + j, bulk.st));
         if (j + 1 < nt) {
-            // mandatory: block column j+1 receives every update k < j it has not seen yet
-            double spent = 0.0;
-            for (int k = done[j + 1]; k < j; ++k) { CKI(apply(k, j + 1, j + 2)); spent += cost(k, j + 1, j + 2); }
-            done[j + 1] = j;
+            // mandatory ops of this step (block column j+1 brought up to date), the event the chain lane's next step
+            // waits for, then the eager ops (plan_left)
+            for (; pi < plan.size() && plan[pi].step == j && plan[pi].mandatory; ++pi)
+                CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
             CKI(step_event(c, j + 1, EV_COL, &ev));
             CK(cudaEventRecord(ev, bulk.st));
-            // eager: spend the rest of this step's share of the remaining update work on the columns behind it, nearest
-            // first, a run of equally advanced columns per launch (this is what balances the lanes: left-looking alone
-            // leaves the bulk lane idle in the first steps and overloads it in the last ones)
-            const double share = c->opts.eager ? remaining / (double)(nt - 1 - j) : 0.0;
-            while (spent < share) {
-                int m = j + 2;
-                while (m < nt && done[m] >= j) ++m;
-                if (m >= nt) break;
-                const int d = done[m];
-                int m1 = m + 1;
-                while (m1 < nt && done[m1] == d) ++m1;
-                const int fit = (int)((share - spent) / cost(d, m, m + 1) + 0.5);
-                if (m1 - m > fit) m1 = m + (fit > 1 ? fit : 1);
-                CKI(apply(d, m, m1));
-                spent += cost(d, m, m1);
-                for (int i = m; i < m1; ++i) done[i] = d + 1;
-            }
-            remaining -= spent;
+            for (; pi < plan.size() && plan[pi].step == j; ++pi) CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
         }
         CKI(mark(c, 6000 + j, bulk.st));
         if (c2 < npad) {
@@ -698,10 +719,17 @@ int prologue_left(mplu_context* c, const double* dA, long long lda) {
         CKI(S.trsm_l(lane, 0, 0, NB, NB, npad));
         CK(cudaEventRecord(c->ev_pro[1], c->side));
     }
-    CKI(launch_first_touch_cols(dA, lda, n, c->W, ld, npad, NB, npad, c->amax, c->rowsum_part, s0, c->nchunk - s0, st));
+    // The cast of the other block columns must leave room on every SM for the second stream's CTAs (a GEMM CTA needs
+    // 320 threads, diag_lu 512): about 5 blocks of 256 threads per SM instead of the 8 that would otherwise be resident
+    // for the whole kernel -- with a full grid every one of tile 0's 61 dependent launches waited for a wave boundary
+    // of the cast and the overlap gained nothing.  768 blocks x 256 threads x 4 loads in flight still saturate HBM.
+    int s1 = (5 * c->num_sms) / ((npad + 255) / 256);
+    if (s1 < 1) s1 = 1;
+    if (s1 > c->nchunk - s0) s1 = c->nchunk - s0;
+    CKI(launch_first_touch_cols(dA, lda, n, c->W, ld, npad, NB, npad, c->amax, c->rowsum_part, s0, s1, st));
     CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB, c->scales + SC_A,
                            bf16, c->status, st));
-    CKI(launch_anorm(c->rowsum_part, n, c->nchunk, c->anorm, st));
+    CKI(launch_anorm(c->rowsum_part, n, s0 + s1, c->anorm, st));
     c->kernel_launches += 3;
     CK(cudaStreamWaitEvent(st, c->ev_pro[1], 0));
     return 0;
@@ -973,7 +1001,7 @@ void mplu_default_options(mplu_options* o) {
     o->side_sms_left = 32;
     o->eager = 1;
     o->stream_c = 1;
-    o->early_scale = 1;
+    o->early_scale = 0;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -1290,6 +1318,23 @@ int mplu_bench_gemm_chain(int variant, int M, int N, int K, int reps, int pdl, i
     cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st); cudaFree(A); cudaFree(B); cudaFree(H); cudaFree(Cm);
     return 0;
+}
+
+// sizes of the interface structs, so that a binding (ctypes, cgo, JNI) can check its mirror of include/mplu.h
+int mplu_sizeof_options(void) { return (int)sizeof(mplu_options); }
+int mplu_sizeof_stats(void) { return (int)sizeof(mplu_stats); }
+
+// The left-looking schedule's bulk-lane plan for an n x n matrix tiled by nb (host logic only, no device needed):
+// (step, k, m0, m1, mandatory) quintuples into out[0 .. 5*max); returns the number of ops.
+int mplu_debug_plan_left(int n, int nb, int eager, int* out, int max) {
+    if (n <= 0 || nb < kDiagBlock || nb % kDiagBlock) return MPLU_E_ARG;
+    const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
+    const std::vector<LeftOp> ops = plan_left(npad, nb > npad ? npad : nb, eager != 0);
+    for (size_t i = 0; i < ops.size() && (int)i < max && out; ++i) {
+        out[5 * i] = ops[i].step; out[5 * i + 1] = ops[i].k; out[5 * i + 2] = ops[i].m0; out[5 * i + 3] = ops[i].m1;
+        out[5 * i + 4] = ops[i].mandatory;
+    }
+    return (int)ops.size();
 }
 
 // development aid: switch timeline marks on (takes effect at the next schedule capture) / read them back as

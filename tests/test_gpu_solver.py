@@ -163,20 +163,27 @@ def test_streamed_host_path_scale_overflow_is_redone(mplu, oracle):
         s.close()
 
 
-def test_early_scale_overflow_is_redone_with_the_global_scale(mplu, oracle, solver):
-    """Device path, left-looking schedule: the first touch overlaps the first diagonal tile, so the fp16 scale comes from
-    the first block column; later block columns 2^6 larger leave the fp16 range under it and the solve must be redone
-    with the global scale -- same answer as asking for the global scale directly, in fp16."""
+def test_early_scale_option(mplu, oracle, solver):
+    """early_scale=1 (left-looking schedule): the first touch overlaps the first diagonal tile, so the fp16 scale comes
+    from the first block column.  Later block columns 2^6 larger leave the fp16 range under it: the overflow is
+    reported (status bit 0) and, had it spoiled the solve, redone with the global scale; the answer must be right
+    either way and agree with the global-scale run."""
     n, nb = 1536, 512
     A = oracle.counter_matrix(n, seed=5)
     A[:, nb:] *= 64.0
     b = A.sum(axis=1)
-    x1, st1 = run(mplu, solver, A, b, nb=nb)
+    x1, st1 = run(mplu, solver, A, b, nb=nb, early_scale=1)
     x0, st0 = run(mplu, solver, A, b, nb=nb, early_scale=0)
-    for st in (st0, st1):
-        assert st["converged"] == 1 and st["status_bits"] == 0 and st["precision_used"] == mplu.MPLU_FP16
-    np.testing.assert_array_equal(x1, x0)
+    assert st0["converged"] == 1 and st0["status_bits"] == 0 and st0["precision_used"] == mplu.MPLU_FP16
+    assert st1["converged"] == 1
+    np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-11)
     np.testing.assert_allclose(x1, 1.0, rtol=0, atol=1e-10)
+    # same matrix without the jump in magnitude: both scale choices are the same power of two, same factors
+    A2 = oracle.counter_matrix(n, seed=5)
+    xa, sa = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=1)
+    xb, sb = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=0)
+    assert sa["status_bits"] == 0 and sb["status_bits"] == 0
+    np.testing.assert_array_equal(xa, xb)
 
 
 def test_spd_kappa_small(mplu, oracle, solver):
@@ -311,7 +318,7 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
             dict(schedule=0, tile_ws=1), dict(schedule=0, side_sms=16, side_sms_early=8), dict(schedule=0, pdl=2))
         left = tuple(dict(schedule=1, **kw) for kw in common) + (
             dict(schedule=1, eager=0), dict(schedule=1, use_graph=0, side_sms_left=64), dict(schedule=1, side_sms_left=16),
-            dict(schedule=1, early_scale=0), dict(schedule=1, early_scale=0, use_graph=0))
+            dict(schedule=1, early_scale=1), dict(schedule=1, early_scale=1, use_graph=0))
         for kw in right + left:
             x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
             LU = s.factors(n)
