@@ -586,7 +586,15 @@ int enqueue_factorization_left(mplu_context* c) {
         CKI(S.getrf(all, 0, 0, NB));
         if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
     }
+    // Two lanes: U(j, j+1), the first thing step j+1 needs, rides in the launch that ends step j on the chain lane
+    // (it is independent of that step's L(j+1, j)); here for j = 0.
+    bool u_done = false;
     if (two) {
+        const int e1 = (2 * NB < npad) ? 2 * NB : npad;
+        CKI(S.trsm_u(all, 0, 0, NB, NB, e1));
+        CKI(step_event(c, 1, EV_U, &ev));
+        CK(cudaEventRecord(ev, st));
+        u_done = true;
         CK(cudaEventRecord(c->ev_fork, st));
         CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     }
@@ -628,15 +636,18 @@ int enqueue_factorization_left(mplu_context* c) {
         const int c2 = (c1 + NB < npad) ? c1 + NB : npad;  // end of tile row j+1
         const int kp = c0 - NB;                             // previous block column [kp, c0)
         // ---- chain lane
-        if (two && j >= 2) {  // the bulk lane gave column j its updates k < j-1
-            CKI(step_event(c, j, EV_COL, &ev));
-            CK(cudaStreamWaitEvent(chain.st, ev, 0));
-        }
         if (!two)  // single lane: plain left-looking, column j receives its updates k < j-1 here
             for (int k = 0; k + 2 <= j; ++k) CKI(apply(k, j, j + 1));
         CKI(mark(c, 1000 + j, chain.st));
-        CKI(S.trsm_u(chain, kp, kp, NB, c0, c1));
-        if (two) { CKI(step_event(c, j, EV_U, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (!u_done) {
+            if (two && j >= 2) {  // the bulk lane gave column j its updates k < j-1
+                CKI(step_event(c, j, EV_COL, &ev));
+                CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            }
+            CKI(S.trsm_u(chain, kp, kp, NB, c0, c1));
+            if (two) { CKI(step_event(c, j, EV_U, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        }
+        u_done = false;
         CKI(S.schur(chain, c0, two ? c1 : npad, c0, c1, kp, c0, (two ? c1 : npad) - c0, w));
         CKI(mark(c, 2000 + j, chain.st));
         CKI(S.getrf(chain, c0, c0, w));
@@ -677,7 +688,14 @@ int enqueue_factorization_left(mplu_context* c) {
         if (c1 < npad) {
             CKI(step_event(c, j, EV_B1, &ev));
             CK(cudaStreamWaitEvent(chain.st, ev, 0));
-            CKI(S.trsm_l(chain, c0, c0, w, c1, c2));
+            // ... and block column j+1 its updates k < j (recorded above, well before GETRF(D_j) ended): L(j+1,j) and
+            // U(j,j+1) share one launch
+            CKI(step_event(c, j + 1, EV_COL, &ev));
+            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(run_gemm_pair(c, chain, S.trsm_l_call(c0, c0, w, c1, c2), S.trsm_u_call(c0, c0, w, c1, c2)));
+            CKI(step_event(c, j + 1, EV_U, &ev));
+            CK(cudaEventRecord(ev, chain.st));
+            u_done = true;
         }
     }
     if (two) {
