@@ -23,6 +23,10 @@ NVCC_FLAGS = [
     "-I", str(ROOT / "include"),
 ]
 
+# experiments: extra nvcc flags from the environment (e.g. MPLU_EXTRA_NVCC_FLAGS="-DMPLU_LEAF_LOOKAHEAD=1"); they are part
+# of the build stamp, so a plain build() afterwards rebuilds the default library
+NVCC_FLAGS += os.environ.get("MPLU_EXTRA_NVCC_FLAGS", "").split()
+
 SOURCES = ["gemm_tc.cu", "panel.cu", "ir.cu", "lu.cu", "gmres.cu", "dist.cu", "generate.cu", "mpf_compat.cu"]
 
 
