@@ -157,6 +157,12 @@ int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *
  * Returns the number of ops; at most `max` are written to out[0 .. 5*max). */
 int mplu_debug_plan_left(int n, int nb, int eager, int *out, int max);
 
+/* Dry run of the device factorization schedule (host logic only, no device needed): every launch with the lane it
+ * runs on and the array regions it reads / writes, and every cross-lane event record / wait, serialised as ints (see
+ * csrc/lu.cu).  Returns the number of ints of the full trace; at most `max` are written.  tests/test_schedule_trace.py
+ * replays it with vector clocks to prove the schedule free of read-after-write / write-after-read races. */
+int mplu_debug_trace(int n, int nb, const mplu_options *opts, int *out, int max);
+
 /* r = b - A x in fp64; norms[0] = ||r||_inf, norms[1] = ||x||_inf (device array of 2 doubles). */
 int mplu_residual(int n, const double *dA, long long lda, const double *dx, const double *db, double *dr,
                   double *dnorms, void *stream);

@@ -107,6 +107,98 @@ void resolve_options(mplu_context* c, int n) {
     if (c->opts.nb <= 0) c->opts.nb = n >= 12288 ? 2048 : (n >= 4096 ? 1024 : 512);
 }
 
+// ---- dry-run trace (mplu_debug_trace): with c->trace set, the schedule functions record what they WOULD launch --
+// every GEMM problem / leaf / cast with the array regions it reads and writes, every event record / wait -- instead of
+// launching it.  tests/test_schedule_trace.py replays the trace with vector clocks and checks that every access
+// happens-after the accesses it conflicts with: a missing or mis-ordered cross-lane event shows up on the CPU, without
+// having to lose a timing-dependent race on a GPU first.
+enum TraceKind : int { TK_GEMM = 0, TK_LEAF = 1, TK_RECORD = 2, TK_WAIT = 3, TK_CAST = 4, TK_MEMSET = 5 };
+enum TraceArray : int { TA_W = 0, TA_WH = 1, TA_FH = 2, TA_LINV = 3, TA_UINV = 4, TA_T1 = 5, TA_T2 = 6 };
+
+int trace_stream(const mplu_context* c, cudaStream_t st) { return st == c->stream ? 0 : 1; }
+
+void trace_push(mplu_context* c, int kind, cudaStream_t st, int ev, int group, const std::vector<TraceRegion>& regs) {
+    TraceOp op;
+    op.kind = kind; op.stream = trace_stream(c, st); op.ev = ev; op.group = group; op.regs = regs;
+    c->trace->push_back(op);
+}
+
+// which 16-bit array a (fake, dry-run) pointer lies in, and its (row, col) there for leading dimension ld
+bool trace_locate16(const mplu_context* c, const void* p, long long ld, int* arr, int* r, int* col) {
+    struct { const uint16_t* base; int id; size_t elems; } tab[] = {
+        {c->Wh, TA_WH, (size_t)c->npad * c->npad}, {c->Fh, TA_FH, (size_t)c->npad * c->npad},
+        {c->Linv16, TA_LINV, (size_t)c->cap_nb * c->npad}, {c->Uinv16, TA_UINV, (size_t)c->cap_nb * c->npad},
+        {c->Tb1, TA_T1, (size_t)c->cap_nb * c->cap_nb}, {c->Tb2, TA_T2, (size_t)c->cap_nb * c->cap_nb}};
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+    for (auto& t : tab)
+        if (q >= t.base && q < t.base + t.elems) {
+            const long long off = q - t.base;
+            *arr = t.id; *r = (int)(off % ld); *col = (int)(off / ld);
+            return true;
+        }
+    return false;
+}
+
+int trace_operand(const mplu_context* c, const Operand16* o) {
+    if (o == &c->opWh) return TA_WH;
+    if (o == &c->opFh) return TA_FH;
+    if (o == &c->opLinv) return TA_LINV;
+    if (o == &c->opUinv) return TA_UINV;
+    if (o == &c->opT1) return TA_T1;
+    return TA_T2;
+}
+
+void trace_gemm(mplu_context* c, const Lane& ln, const GemmCall& g, int group) {
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return;
+    std::vector<TraceRegion> regs;
+    regs.push_back({trace_operand(c, g.A), g.a_r0, g.a_r0 + g.M, g.a_c0, g.a_c0 + g.K, 0});
+    regs.push_back({trace_operand(c, g.B), g.b_r0, g.b_r0 + g.K, g.b_c0, g.b_c0 + g.N, 0});
+    if (g.C) {
+        const long long off = g.C - c->W;
+        const int r = (int)(off % g.ldc), col = (int)(off / g.ldc);
+        if (g.accumulate) regs.push_back({TA_W, r, r + g.M, col, col + g.N, 0});
+        regs.push_back({TA_W, r, r + g.M, col, col + g.N, 1});
+    }
+    if (g.H) {
+        int arr = 0, r = 0, col = 0;
+        if (trace_locate16(c, g.H, g.ldh, &arr, &r, &col)) {
+            const int hr = g.h_rows < g.M ? g.h_rows : g.M, hc = g.h_cols < g.N ? g.h_cols : g.N;
+            if (hr > 0) regs.push_back({arr, r, r + hr, col, col + g.N, 1});
+            if (hc > 0 && hr < g.M) regs.push_back({arr, r + hr, r + g.M, col, col + hc, 1});
+        }
+    }
+    trace_push(c, TK_GEMM, ln.st, -1, group, regs);
+}
+
+// event handles of a dry run are just numbers; real runs go to CUDA
+int ev_record(mplu_context* c, cudaEvent_t ev, cudaStream_t st) {
+    if (c->trace) { trace_push(c, TK_RECORD, st, (int)(uintptr_t)ev, -1, {}); return 0; }
+    return (int)cudaEventRecord(ev, st);
+}
+int ev_wait(mplu_context* c, cudaStream_t st, cudaEvent_t ev) {
+    if (c->trace) { trace_push(c, TK_WAIT, st, (int)(uintptr_t)ev, -1, {}); return 0; }
+    return (int)cudaStreamWaitEvent(st, ev, 0);
+}
+int traced_cast(mplu_context* c, int r0, int c0, int rows, int cols, cudaStream_t st) {  // Wh block <- W block
+    const long long ld = c->npad;
+    if (c->trace) {
+        if (rows > 0 && cols > 0)
+            trace_push(c, TK_CAST, st, -1, -1, {{TA_W, r0, r0 + rows, c0, c0 + cols, 0}, {TA_WH, r0, r0 + rows, c0, c0 + cols, 1}});
+        return 0;
+    }
+    return launch_shadow_cast(c->W + r0 + c0 * ld, ld, c->Wh + r0 + c0 * ld, ld, rows, cols, c->scales + SC_A,
+                              c->opts.precision == MPLU_BF16, c->status, st);
+}
+int traced_clear_bands(mplu_context* c, cudaStream_t st) {
+    if (c->trace) {
+        trace_push(c, TK_MEMSET, st, -1, -1, {{TA_LINV, 0, c->cap_nb, 0, c->npad, 1}, {TA_UINV, 0, c->cap_nb, 0, c->npad, 1}});
+        return 0;
+    }
+    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * c->npad * sizeof(uint16_t), st));
+    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * c->npad * sizeof(uint16_t), st));
+    return 0;
+}
+
 // programmatic dependent launch: everywhere (opts.pdl == 1) or on the chain lane only (opts.pdl == 2)
 inline int lane_pdl(const mplu_context* c, const Lane& ln) { return c->opts.pdl == 1 || (c->opts.pdl == 2 && ln.pdl); }
 
@@ -145,6 +237,7 @@ int lane_sms(const mplu_context* c, const Lane& ln) {
 
 int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    if (c->trace) { trace_gemm(c, ln, g, c->trace_group++); c->gemm_launches++; c->kernel_launches++; return 0; }
     const int variant = pick_variant(c, g);
     const bool cg2 = (variant == GEMM_CG2_AMN);
     const GemmParams p = gemm_params(c, g, ln);
@@ -158,6 +251,12 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
     const bool e0 = g0.M <= 0 || g0.N <= 0 || g0.K <= 0, e1 = g1.M <= 0 || g1.N <= 0 || g1.K <= 0;
     if (e0) return e1 ? 0 : run_gemm(c, ln, g1);
     if (e1) return run_gemm(c, ln, g0);
+    if (c->trace && c->opts.group && pick_variant(c, g0) == pick_variant(c, g1)) {  // one launch: the two are concurrent
+        const int grp = c->trace_group++;
+        trace_gemm(c, ln, g0, grp); trace_gemm(c, ln, g1, grp);
+        c->gemm_launches++; c->kernel_launches++;
+        return 0;
+    }
     const int variant = pick_variant(c, g0);
     if (!c->opts.group || variant != pick_variant(c, g1)) {
         CKI(run_gemm(c, ln, g0));
@@ -186,6 +285,12 @@ int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int c
     if (variant < 0) return 0;
     if (!uniform) {
         for (int i = 0; i < count; ++i) CKI(run_gemm(c, ln, calls[i]));
+        return 0;
+    }
+    if (c->trace) {  // one launch: its problems are concurrent
+        const int grp = c->trace_group++;
+        for (int i = 0; i < count; ++i) trace_gemm(c, ln, calls[i], grp);
+        c->gemm_launches++; c->kernel_launches++;
         return 0;
     }
     const bool cg2 = (variant == GEMM_CG2_AMN);
@@ -255,6 +360,14 @@ struct Sched {
             const int blk = c0 / kDiagBlock;
             uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
             uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
+            if (c->trace) {  // reads and rewrites its W block, writes its triangles of the two inverse bands
+                trace_push(c, TK_LEAF, ln.st, -1, -1,
+                           {{TA_W, c0, c0 + kDiagBlock, c0, c0 + kDiagBlock, 0}, {TA_W, c0, c0 + kDiagBlock, c0, c0 + kDiagBlock, 1},
+                            {TA_LINV, c0 - T, c0 - T + kDiagBlock, c0, c0 + kDiagBlock, 1},
+                            {TA_UINV, c0 - T, c0 - T + kDiagBlock, c0, c0 + kDiagBlock, 1}});
+                c->kernel_launches++;
+                return 0;
+            }
             CKI(mark(c, 8000 + blk, ln.st));  // development aid (mplu_debug_marks_enable): leaf start / end
             CKI(launch_diag_lu(c->W, ld, c0, l16, u16, ldi, c->Linv32, c->Uinv32, ts(T), c0 == T, blk,
                                c->opts.precision == MPLU_BF16, c->status, ln.st, nullptr, lane_pdl(c, ln),
@@ -360,12 +473,14 @@ int prepare_tile_workspace(mplu_context* c, int NB, cudaStream_t getrf_stream) {
 }
 
 int record_event(mplu_context* c, cudaEvent_t ev, cudaStream_t st) {
+    if (c->trace) return 0;
     return (int)cudaEventRecordWithFlags(ev, st, c->capturing ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
 // timeline mark: tag = 1000*kind + step; kinds: 1 chain: next-tile TRSM start, 2 chain: GETRF start, 3 chain: GETRF end,
 // 4 bulk: TRSM start, 5 bulk: block column/row update start, 6 bulk: rest start, 7 bulk: rest end
 int mark(mplu_context* c, int tag, cudaStream_t st) {
+    if (c->trace) return 0;
     if (!c->marks_on || c->mark_count >= mplu_context::kMaxMarks) return 0;
     cudaEvent_t& e = c->mark_ev[c->mark_count];
     if (!e) CK(cudaEventCreate(&e));
@@ -375,6 +490,7 @@ int mark(mplu_context* c, int tag, cudaStream_t st) {
 
 int step_event(mplu_context* c, int step, int kind, cudaEvent_t* out) {
     if (step >= mplu_context::kMaxSteps) return MPLU_E_ARG;
+    if (c->trace) { *out = (cudaEvent_t)(uintptr_t)(1000 + 4 * step + kind); return 0; }
     cudaEvent_t& e = c->ev_step[4 * step + kind];
     if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = e;
@@ -404,22 +520,20 @@ int enqueue_factorization(mplu_context* c) {
     enum { EV_GETRF = 0, EV_NEXT = 1, EV_B2 = 2, EV_B3A = 3 };
     cudaEvent_t ev = nullptr;
 
-    CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
-    CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+    if (!c->trace) CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+    CKI(traced_cast(c, 0, 0, npad, NB, st));
     if (npad > NB)
-        CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
-                               c->scales + SC_A, bf16, c->status, st));
+        CKI(traced_cast(c, 0, NB, NB, npad - NB, st));
     c->kernel_launches += 3;
     // the inverse bands are only ever written inside the diagonal tiles' triangles: everything else must read 0
-    CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
-    CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CKI(traced_clear_bands(c, st));
 
     const bool ws = c->opts.tile_ws != 0 && npad > NB;
     if (ws) CK(cudaMemcpyAsync(c->tile->scales, c->scales, SC_COUNT * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (ws) CKI(getrf_in_workspace(c, all, 0, NB)); else CKI(S.getrf(all, 0, 0, NB));
     if (two) {
-        CK(cudaEventRecord(c->ev_fork, st));
-        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        CKI(ev_record(c, c->ev_fork, st));
+        CKI(ev_wait(c, c->side, c->ev_fork));
     }
     int step = 0;
     for (int k0 = 0; k0 + NB < npad; k0 += NB, ++step) {
@@ -440,42 +554,42 @@ int enqueue_factorization(mplu_context* c) {
         // ---- chain lane: panel solves restricted to the next tile, its Schur update, its GETRF
         if (two && step > 0) {  // tile rows/columns k1.. of block column/row k were updated by the bulk lane
             CKI(step_event(c, step - 1, EV_B2, &ev));
-            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(ev_wait(c, chain.st, ev));
         }
         CKI(mark(c, 1000 + step, chain.st));
         CKI(S.trsm_lu(chain, k0, k0, NB, k1, k2));
-        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CKI(ev_record(c, ev, chain.st)); }
         if (two && step > 0) {  // the next diagonal tile has received update step-1 (first piece of the bulk's rest)
             CKI(step_event(c, step - 1, EV_B3A, &ev));
-            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(ev_wait(c, chain.st, ev));
         }
         CKI(S.schur(chain, k1, k2, k1, k2, k0, k1, nbn, nbn));
         CKI(mark(c, 2000 + step, chain.st));
         if (ws) CKI(getrf_in_workspace(c, chain, k1, nbn)); else CKI(S.getrf(chain, k1, k1, nbn));
         CKI(mark(c, 3000 + step, chain.st));
-        if (two) { CKI(step_event(c, step + 1, EV_GETRF, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (two) { CKI(step_event(c, step + 1, EV_GETRF, &ev)); CKI(ev_record(c, ev, chain.st)); }
         // ---- bulk lane: the other rows/columns of the panels, then the trailing update
         if (k2 >= npad) continue;
         if (two && step > 0) {  // GETRF of tile k (its inverses) came from the chain lane
             CKI(step_event(c, step, EV_GETRF, &ev));
-            CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+            CKI(ev_wait(c, bulk.st, ev));
         }
         CKI(mark(c, 4000 + step, bulk.st));
         CKI(S.trsm_lu(bulk, k0, k0, NB, k2, npad));
-        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CK(cudaStreamWaitEvent(bulk.st, ev, 0)); }
+        if (two) { CKI(step_event(c, step, EV_NEXT, &ev)); CKI(ev_wait(c, bulk.st, ev)); }
         CKI(mark(c, 5000 + step, bulk.st));
         // next block column and next block row (full shadows), one grouped launch
         CKI(run_gemm_pair(c, bulk, S.schur_call(k2, npad, k1, k2, k0, k1, npad - k2, nbn),
                           S.schur_call(k1, k2, k2, npad, k0, k1, nbn, npad - k2)));
-        if (two) { CKI(step_event(c, step, EV_B2, &ev)); CK(cudaEventRecord(ev, bulk.st)); }
+        if (two) { CKI(step_event(c, step, EV_B2, &ev)); CKI(ev_record(c, ev, bulk.st)); }
         // the rest of the trailing matrix (no shadow), block column k2.. first: the chain lane's next Schur update
         // only needs the diagonal tile inside it
         const int k3 = (k2 + NB < npad) ? k2 + NB : npad;
         CKI(S.schur(bulk, k2, npad, k2, k3, k0, k1, 0, 0));
-        if (two) { CKI(step_event(c, step, EV_B3A, &ev)); CK(cudaEventRecord(ev, bulk.st)); }
+        if (two) { CKI(step_event(c, step, EV_B3A, &ev)); CKI(ev_record(c, ev, bulk.st)); }
         if (k3 >= npad) continue;
         const int Mt = npad - k2, Nt = npad - k3;
-        const bool timed = c->trail_count < mplu_context::kMaxTrail;
+        const bool timed = !c->trace && c->trail_count < mplu_context::kMaxTrail;
         if (timed) {
             cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
             if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
@@ -492,8 +606,8 @@ int enqueue_factorization(mplu_context* c) {
         }
     }
     if (two) {
-        CK(cudaEventRecord(c->ev_join, c->side));
-        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        CKI(ev_record(c, c->ev_join, c->side));
+        CKI(ev_wait(c, st, c->ev_join));
     }
     return 0;
 }
@@ -575,14 +689,12 @@ int enqueue_factorization_left(mplu_context* c) {
     cudaEvent_t ev = nullptr;
 
     if (!c->prologue_done) {  // else prologue_left() has done this part, overlapped with the first touch
-        CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
-        CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
+        if (!c->trace) CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
+        CKI(traced_cast(c, 0, 0, npad, NB, st));
         if (npad > NB)
-            CKI(launch_shadow_cast(c->W + (long long)NB * ld, ld, c->Wh + (long long)NB * ld, ld, NB, npad - NB,
-                                   c->scales + SC_A, bf16, c->status, st));
+            CKI(traced_cast(c, 0, NB, NB, npad - NB, st));
         c->kernel_launches += 3;
-        CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
-        CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+        CKI(traced_clear_bands(c, st));
         CKI(S.getrf(all, 0, 0, NB));
         if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
     }
@@ -593,10 +705,10 @@ int enqueue_factorization_left(mplu_context* c) {
         const int e1 = (2 * NB < npad) ? 2 * NB : npad;
         CKI(S.trsm_u(all, 0, 0, NB, NB, e1));
         CKI(step_event(c, 1, EV_U, &ev));
-        CK(cudaEventRecord(ev, st));
+        CKI(ev_record(c, ev, st));
         u_done = true;
-        CK(cudaEventRecord(c->ev_fork, st));
-        CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        CKI(ev_record(c, c->ev_fork, st));
+        CKI(ev_wait(c, c->side, c->ev_fork));
     }
     // the bulk lane's tall updates: rows r0.. of block columns [c0, c1), full shadow
     // `last`: this is the block columns' final update (k = column - 1): everything below gets its 16-bit shadow (the
@@ -608,7 +720,7 @@ int enqueue_factorization_left(mplu_context* c) {
     };
     auto timed_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1) -> int {
         // every rank-nb update of the bulk lane is timed with its own event pair for the roofline figure
-        const bool timed = c->trail_count < mplu_context::kMaxTrail;
+        const bool timed = !c->trace && c->trail_count < mplu_context::kMaxTrail;
         if (timed) {
             cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
             if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
@@ -642,29 +754,29 @@ int enqueue_factorization_left(mplu_context* c) {
         if (!u_done) {
             if (two && j >= 2) {  // the bulk lane gave column j its updates k < j-1
                 CKI(step_event(c, j, EV_COL, &ev));
-                CK(cudaStreamWaitEvent(chain.st, ev, 0));
+                CKI(ev_wait(c, chain.st, ev));
             }
             CKI(S.trsm_u(chain, kp, kp, NB, c0, c1));
-            if (two) { CKI(step_event(c, j, EV_U, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+            if (two) { CKI(step_event(c, j, EV_U, &ev)); CKI(ev_record(c, ev, chain.st)); }
         }
         u_done = false;
         CKI(S.schur(chain, c0, two ? c1 : npad, c0, c1, kp, c0, (two ? c1 : npad) - c0, w));
         CKI(mark(c, 2000 + j, chain.st));
         CKI(S.getrf(chain, c0, c0, w));
         CKI(mark(c, 3000 + j, chain.st));
-        if (two) { CKI(step_event(c, j, EV_G, &ev)); CK(cudaEventRecord(ev, chain.st)); }
+        if (two) { CKI(step_event(c, j, EV_G, &ev)); CKI(ev_record(c, ev, chain.st)); }
         if (!two) {
             if (c1 < npad) CKI(S.trsm_l(chain, c0, c0, w, c1, npad));
             continue;
         }
         // ---- bulk lane
         CKI(step_event(c, j, EV_U, &ev));
-        CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+        CKI(ev_wait(c, bulk.st, ev));
         CKI(mark(c, 4000 + j, bulk.st));
         if (c1 < npad) {
             CKI(big_schur(bulk, c1, c0, c1, kp, c0, true));
             CKI(step_event(c, j, EV_B1, &ev));
-            CK(cudaEventRecord(ev, bulk.st));
+            CKI(ev_record(c, ev, bulk.st));
         }
         CKI(mark(c, 5000 + j, bulk.st));
         if (j + 1 < nt) {
@@ -673,13 +785,13 @@ int enqueue_factorization_left(mplu_context* c) {
             for (; pi < plan.size() && plan[pi].step == j && plan[pi].mandatory; ++pi)
                 CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
             CKI(step_event(c, j + 1, EV_COL, &ev));
-            CK(cudaEventRecord(ev, bulk.st));
+            CKI(ev_record(c, ev, bulk.st));
             for (; pi < plan.size() && plan[pi].step == j; ++pi) CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
         }
         CKI(mark(c, 6000 + j, bulk.st));
         if (c2 < npad) {
             CKI(step_event(c, j, EV_G, &ev));
-            CK(cudaStreamWaitEvent(bulk.st, ev, 0));
+            CKI(ev_wait(c, bulk.st, ev));
             CKI(S.trsm_l(bulk, c0, c0, w, c2, npad));
         }
         CKI(mark(c, 7000 + j, bulk.st));
@@ -687,20 +799,20 @@ int enqueue_factorization_left(mplu_context* c) {
         // order to be captured): tile j+1 of column j has received update j-1 from the bulk lane long before
         if (c1 < npad) {
             CKI(step_event(c, j, EV_B1, &ev));
-            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(ev_wait(c, chain.st, ev));
             // ... and block column j+1 its updates k < j (recorded above, well before GETRF(D_j) ended): L(j+1,j) and
             // U(j,j+1) share one launch
             CKI(step_event(c, j + 1, EV_COL, &ev));
-            CK(cudaStreamWaitEvent(chain.st, ev, 0));
+            CKI(ev_wait(c, chain.st, ev));
             CKI(run_gemm_pair(c, chain, S.trsm_l_call(c0, c0, w, c1, c2), S.trsm_u_call(c0, c0, w, c1, c2)));
             CKI(step_event(c, j + 1, EV_U, &ev));
-            CK(cudaEventRecord(ev, chain.st));
+            CKI(ev_record(c, ev, chain.st));
             u_done = true;
         }
     }
     if (two) {
-        CK(cudaEventRecord(c->ev_join, c->side));
-        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        CKI(ev_record(c, c->ev_join, c->side));
+        CKI(ev_wait(c, st, c->ev_join));
     }
     return 0;
 }
@@ -1336,6 +1448,51 @@ int mplu_bench_gemm_chain(int variant, int M, int N, int K, int reps, int pdl, i
     cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaStreamDestroy(st); cudaFree(A); cudaFree(B); cudaFree(H); cudaFree(Cm);
     return 0;
+}
+
+// Dry run of the device factorization schedule for an n x n matrix (host logic only, no device needed): what would be
+// launched on which lane, which array regions each launch reads / writes, and every cross-lane event record / wait.
+// Serialised as ints: per op  kind, stream, event, group, nregions, then nregions x (array, r0, r1, c0, c1, write).
+// Returns the number of ints the full trace needs (at most `max` are written).
+int mplu_debug_trace(int n, int nb, const mplu_options* opts, int* out, int max) {
+    if (n <= 0) return MPLU_E_ARG;
+    mplu_context* c = new (std::nothrow) mplu_context();
+    if (!c) return MPLU_E_ARG;
+    if (opts) c->opts = *opts; else mplu_default_options(&c->opts);
+    c->opts.nb = nb;
+    c->opts.tile_ws = 0;
+    resolve_options(c, n);
+    c->n = n;
+    c->npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
+    c->cap_npad = c->npad;
+    c->cap_nb = effective_nb(c, c->npad);
+    c->num_sms = 148;
+    // fake, never dereferenced: distinct address ranges so that a pointer identifies its array
+    c->W = reinterpret_cast<float*>(1ull << 44);
+    c->Wh = reinterpret_cast<uint16_t*>(2ull << 44);
+    c->Fh = reinterpret_cast<uint16_t*>(3ull << 44);
+    c->Linv16 = reinterpret_cast<uint16_t*>(4ull << 44);
+    c->Uinv16 = reinterpret_cast<uint16_t*>(5ull << 44);
+    c->Tb1 = reinterpret_cast<uint16_t*>(6ull << 44);
+    c->Tb2 = reinterpret_cast<uint16_t*>(7ull << 44);
+    c->scales = reinterpret_cast<float*>(8ull << 44);
+    c->inv_scales = reinterpret_cast<float*>(9ull << 44);
+    c->stream = reinterpret_cast<cudaStream_t>(1);
+    c->side = reinterpret_cast<cudaStream_t>(2);
+    c->ev_fork = reinterpret_cast<cudaEvent_t>(900000);
+    c->ev_join = reinterpret_cast<cudaEvent_t>(900001);
+    std::vector<TraceOp> tr;
+    c->trace = &tr;
+    const int rc = c->opts.schedule == MPLU_SCHED_LEFT ? enqueue_factorization_left(c) : enqueue_factorization(c);
+    delete c;
+    if (rc) return rc < 0 ? rc : -rc;
+    long long pos = 0;
+    auto put = [&](int v) { if (out && pos < max) out[pos] = v; ++pos; };
+    for (const TraceOp& op : tr) {
+        put(op.kind); put(op.stream); put(op.ev); put(op.group); put((int)op.regs.size());
+        for (const TraceRegion& r : op.regs) { put(r.arr); put(r.r0); put(r.r1); put(r.c0); put(r.c1); put(r.write); }
+    }
+    return (int)pos;
 }
 
 // sizes of the interface structs, so that a binding (ctypes, cgo, JNI) can check its mirror of include/mplu.h

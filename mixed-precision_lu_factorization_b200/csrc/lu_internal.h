@@ -5,6 +5,12 @@
 #include "gemm_tc.h"
 #include "kernels.h"
 
+#include <vector>
+
+// dry-run trace of a schedule (lu.cu: trace_*; tests/test_schedule_trace.py)
+struct TraceRegion { int arr, r0, r1, c0, c1, write; };
+struct TraceOp { int kind, stream, ev, group; std::vector<TraceRegion> regs; };
+
 struct mplu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -52,6 +58,9 @@ struct mplu_context {
     // left-looking prologue (first touch overlapped with the first diagonal tile)
     cudaEvent_t ev_pro[2] = {nullptr, nullptr};
     bool prologue_done = false, used_early_scale = false, allow_early = true;
+    // dry run: non-null = record the schedule instead of launching it
+    std::vector<TraceOp>* trace = nullptr;
+    int trace_group = 0;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {
         uint16_t* base = nullptr;
