@@ -88,7 +88,7 @@ def cpu_lapack_baseline(n_sample):
     import numpy as np
     import mplu_oracle as orc
     from scipy.linalg import lu_factor, lu_solve
-    A = orc.counter_matrix(n_sample, seed=1)
+    A = orc.counter_matrix_into(np.empty((n_sample, n_sample), order="F"), seed=1)
     b = A.sum(axis=1)
     lu_factor(A[:512, :512].copy())  # thread-pool warm-up
     t = time.perf_counter()
@@ -119,8 +119,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mplu_oracle as orc
     n = args.n or 32768
-    n_cpu = min(n, 8192)
-    cpu = cpu_lapack_baseline(n_cpu)
+    cpu = cpu_lapack_baseline(min(n, args.cpu_n))
     line = dict(impl="reference", metric=METRIC, unit="TFLOP/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=f"n={n} column-diagonally-dominant, reference MPF(A,n,32,ipiv) LU only (it has no solve)"))
@@ -136,12 +135,16 @@ def run_reference(args):
         f = getattr(lib, "_Z3MPFPdiiPi")
         f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         f.restype = None
-        n_ref = min(n, args.ref_n)
-        A0 = np.asfortranarray(orc.counter_matrix(n_ref, seed=1))
+        import torch
+        n_ref = min(n, args.ref_n) if args.ref_n > 0 else n  # default: the repo arm's own n (same config)
+        # the same generated input as the repo arm (mplu_generate == oracle.counter_matrix), built by column blocks
+        A0 = np.empty((n_ref, n_ref), dtype=np.float64, order="F")
+        orc.counter_matrix_into(A0, seed=1)
+        A = np.empty_like(A0, order="F")
         devnull = os.open(os.devnull, os.O_WRONLY)
         times = []
         for it in range(args.warmup + args.steps):
-            A = A0.copy(order="F")
+            torch.from_numpy(A.T).copy_(torch.from_numpy(A0.T))  # MPF factors in place: fresh input every call (threaded copy)
             ipiv = np.arange(1, n_ref + 1, dtype=np.int32)
             sys.stdout.flush()
             saved = os.dup(1)
@@ -294,8 +297,8 @@ def main():
     ap.add_argument("--nb", type=int, default=0, help="outer block size (0 = library default for this n)")
     ap.add_argument("--precision", choices=["fp16", "bf16"], default="fp16")
     ap.add_argument("--impl", choices=["mplu", "reference"], default="mplu")
-    ap.add_argument("--ref-n", type=int, default=16384, help="size the reference arm runs (bounded: it needs seconds per call)")
-    ap.add_argument("--cpu-n", type=int, default=8192, help="sample size of the cpu_baseline leg")
+    ap.add_argument("--ref-n", type=int, default=0, help="size the reference arm runs (0 = the same n as the repo arm; the reference needs seconds per call)")
+    ap.add_argument("--cpu-n", type=int, default=16384, help="sample size of the host LAPACK cpu_baseline leg (bounded: ~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -46,7 +46,7 @@ typedef struct mplu_options {
     int a_exp;        /* fp16 only: A-type shadows are scaled so max|A| maps into (2^(a_exp-1), 2^a_exp]; default 11 */
     int l_exp;        /* fp16 only: multipliers are scaled by 2^l_exp; default 11 */
     int lookahead;    /* 1 (default): factor panel k+1 on a second stream while the rest of update k runs */
-    int side_sms;     /* SMs of the chain lane (diagonal-tile GETRF + next-tile solves), default 32 */
+    int side_sms;     /* MPLU_SCHED_RIGHT: SMs of the chain lane (diagonal-tile GETRF + next-tile solves), default 40 */
     int use_graph;    /* 1 (default): capture the factorization schedule once per (n, options) into a CUDA graph */
     int pdl;          /* 1: programmatic dependent launches along each stream's kernel chain (default 0: measured slower,
                          pre-launched CTAs take SMs from the other lane); 2: on the chain lane only */

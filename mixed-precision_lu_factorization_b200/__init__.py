@@ -383,6 +383,23 @@ def generate(n, seed=1, dominant=True, with_rhs=True):
     return A, b
 
 
+def generate_spd(n, kappa, seed=1):
+    """Device-resident SPD test matrix A = H diag(sigma) H, H = I - 2uu^T, sigma geometric in [1/kappa, 1] (the
+    condition-number sweep of BASELINE.json configs[4]; same construction as the oracle's spd_kappa_matrix, built in
+    O(n^2) on the device).  Symmetric, so its row-major storage is also its column-major storage."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    u = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    u /= u.norm()
+    sig = kappa ** (-torch.arange(n, dtype=torch.float64, device="cuda") / max(n - 1, 1))
+    du = sig * u
+    A = torch.diag(sig)
+    A -= 2.0 * torch.outer(u, du)
+    A -= 2.0 * torch.outer(du, u)
+    A += 4.0 * torch.dot(u, du) * torch.outer(u, u)
+    return A
+
+
 def MPF(A, r=32, ipiv=None):
     """Reference-compatible entry point (/root/reference/MPF.h:3): factor the column-major fp64 HOST matrix `A`
     (numpy, Fortran order, modified in place) with panel width r; returns the 1-based pivot vector."""

@@ -755,6 +755,8 @@ int mplu_dist_unique_id(void* id128) {
     return 0;
 }
 
+void mplu_dist_destroy(mplu_dist* d);
+
 static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
     d->device = device;
     d->P = P;
@@ -787,14 +789,20 @@ int mplu_dist_create(mplu_dist** out, int device, int rank, int nranks, int P, i
     d->ranks.resize(1);
     d->ranks[0].p = rank / Q;
     d->ranks[0].q = rank % Q;
-    int rc = dist_create_common(d, device, P, Q);
-    if (rc) return rc;
-    ncclUniqueId id;
-    memcpy(&id, id128, sizeof(id));
-    NK(api->CommInitRank(&d->world, nranks, id, rank));
-    // process row p: ranks (p, *) ordered by q; process column q: ranks (*, q) ordered by p
-    NK(api->CommSplit(d->world, d->ranks[0].p, d->ranks[0].q, &d->rowc, nullptr));
-    NK(api->CommSplit(d->world, d->ranks[0].q, d->ranks[0].p, &d->colc, nullptr));
+    // Every rank joins the communicators even when its own device set-up failed (a rank that returned early would
+    // leave its peers hung inside the collective ncclCommInitRank); the failure is reported after that.
+    const int rc = dist_create_common(d, device, P, Q);
+    auto comms = [&]() -> int {
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NK(api->CommInitRank(&d->world, nranks, id, rank));
+        // process row p: ranks (p, *) ordered by q; process column q: ranks (*, q) ordered by p
+        NK(api->CommSplit(d->world, d->ranks[0].p, d->ranks[0].q, &d->rowc, nullptr));
+        NK(api->CommSplit(d->world, d->ranks[0].q, d->ranks[0].p, &d->colc, nullptr));
+        return 0;
+    };
+    const int rc2 = comms();
+    if (rc || rc2) { mplu_dist_destroy(d); return rc ? rc : rc2; }
     *out = d;
     return 0;
 }
@@ -811,8 +819,8 @@ int mplu_dist_create_local(mplu_dist** out, int device, int P, int Q) {
             d->ranks[(size_t)p * Q + q].p = p;
             d->ranks[(size_t)p * Q + q].q = q;
         }
-    int rc = dist_create_common(d, device, P, Q);
-    if (rc) return rc;
+    const int rc = dist_create_common(d, device, P, Q);
+    if (rc) { mplu_dist_destroy(d); return rc; }
     *out = d;
     return 0;
 }

@@ -1,8 +1,7 @@
 // Trailing-update GEMM on the 5th-generation tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma kind::f16 issued by one thread
 //   -> fp32 accumulators in TMEM (2 x 256 columns, double buffered) -> tcgen05.ld epilogue that applies
-//   C <- C + alpha*acc in fp32 (optionally taking the addend from the original fp64 matrix on first touch) and
-//   emits the scaled 16-bit shadow the next panel / TRSM will consume.
+//   C <- C + alpha*acc in fp32 and emits the scaled 16-bit shadow the next panel / TRSM will consume.
 //
 // Replaces the rank-r cublasDgemm / cublasDtrsm pair of the reference (/root/reference/MPF.cu:215-239).
 //
@@ -477,14 +476,10 @@ int launch_gemm_group(int variant, GemmGroup& g, int max_sms, cudaStream_t strea
         if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.K % BK != 0 || p.bf16 != g.p[0].bf16) return (int)cudaErrorInvalidValue;
         ragged = ragged || (p.M % 32) || (p.N % 32) || (p.H && (p.h_cols % 32) && p.h_cols < p.N);
     }
-    if (max_sms <= 0) {
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        }
-        max_sms = sms;
+    if (max_sms <= 0) {  // the current device's SM count (an attribute query, cheap; never cached across devices)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     // aligned fast path: whole 32 x 32 epilogue chunks (the factorization only ever issues these)
     if (!ragged) {

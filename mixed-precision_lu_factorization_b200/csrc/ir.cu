@@ -3,6 +3,8 @@
 // structure: r = b - A*x in fp64, L U d = r in the factorization precision, x += d in fp64.
 // All of them are HBM-bound: the residual streams 8*n^2 bytes, the solve pair 4*n^2 bytes.
 #include "kernels.h"
+
+#include <mutex>
 #include "ptx.cuh"
 
 #include <cstdlib>
@@ -340,13 +342,21 @@ int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float*
 int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
                     int mode, cudaStream_t st) {
-    static int max_grid = 0, max_grid_cl = 0;
+    // the dynamic shared-memory opt-in and the co-residency limits are PER DEVICE: cached per device ordinal
+    constexpr int kMaxDev = 64;
+    static int s_max_grid[kMaxDev] = {}, s_max_grid_cl[kMaxDev] = {};
+    static std::mutex s_mu;
     constexpr int CL = 8;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDev) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(s_mu);
+    int& max_grid = s_max_grid[dev];
+    int& max_grid_cl = s_max_grid_cl[dev];
     if (!max_grid) {
         cudaError_t e = cudaFuncSetAttribute(lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSV_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lu_solve_kernel, TSV_THREADS, TSV_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;

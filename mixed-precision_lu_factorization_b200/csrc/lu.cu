@@ -107,6 +107,16 @@ void resolve_options(mplu_context* c, int n) {
     if (c->opts.nb <= 0) c->opts.nb = n >= 12288 ? 2048 : (n >= 4096 ? 1024 : 512);
 }
 
+// c->opts is the caller's REQUEST.  What a call resolves for itself (the nb chosen for this n, the bf16 fallback after an
+// fp16 overflow) lives in c->opts only for the duration of that call; the precision actually used is reported through
+// mplu_stats::precision_used.
+struct OptionsScope {
+    mplu_context* c;
+    mplu_options requested;
+    explicit OptionsScope(mplu_context* ctx) : c(ctx), requested(ctx->opts) {}
+    ~OptionsScope() { c->opts = requested; }
+};
+
 // ---- dry-run trace (mplu_debug_trace): with c->trace set, the schedule functions record what they WOULD launch --
 // every GEMM problem / leaf / cast with the array regions it reads and writes, every event record / wait -- instead of
 // launching it.  tests/test_schedule_trace.py replays the trace with vector clocks and checks that every access
@@ -893,11 +903,14 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
             CKI(prepare_tile_workspace(c, NB, two ? c->side : st));
         }
     }
-    mplu_context::GraphKey key{n, npad, effective_nb(c, npad), c->opts.precision, c->opts.gemm_variant, c->opts.max_sms,
-                               c->opts.lookahead, c->opts.side_sms, c->opts.a_exp, c->opts.l_exp, c->opts.pdl, c->opts.group,
-                               c->opts.tile_ws + 2 * (int)(c->opts.cg2_min_elems >> 8) + (c->opts.side_sms_early << 24) + (c->opts.early_pct << 16) + (c->opts.late_pct << 8) + (c->opts.tri_skip << 1),
-                               c->W, c->tile ? (const void*)c->tile->W : nullptr, c->opts.schedule + 2 * c->opts.eager + 4 * c->opts.stream_c + 8 * (int)early + 16 * c->opts.side_sms_left};
-    const bool hit = use_graph && c->graph_exec && memcmp(&key, &c->gkey, sizeof(key)) == 0;
+    // every option and pointer the captured schedule depends on, one value per slot (no packing, no struct padding)
+    const mplu_options& o = c->opts;
+    const std::vector<long long> key = {
+        n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
+        o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, (long long)early, (long long)c->marks_on,
+        (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
+    const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
         c->gemm_launches = 0;
         c->kernel_launches = early ? 0 : 2;  // first touch + anorm
@@ -917,7 +930,6 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
             e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { c->graph_exec = nullptr; return (int)e; }
-            memset(&c->gkey, 0, sizeof(c->gkey));
             c->gkey = key;
             c->g_gemm_launches = c->gemm_launches; c->g_kernel_launches = c->kernel_launches;
             c->g_trail_count = c->trail_count; c->g_trail_flops = c->trail_flops; c->g_trail_bytes = c->trail_bytes;
@@ -1018,8 +1030,8 @@ __global__ void absmax_kernel(const double* v, int n, double* out) {
 __global__ void widen_kernel(const float* __restrict__ W, long long ldw, int n, double* __restrict__ out,
                              long long ldo) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
-    if (r < n) out[r + (long long)c * ldo] = (double)W[r + (long long)c * ldw];
+    if (r >= n) return;
+    for (int c = blockIdx.y; c < n; c += gridDim.y) out[r + (long long)c * ldo] = (double)W[r + (long long)c * ldw];
 }
 
 int solve_impl(mplu_context* c, const double* dA, long long lda, const double* db, double* dx, mplu_stats* stats) {
@@ -1144,21 +1156,26 @@ int mplu_create(mplu_context** out, int device) {
     if (!c) return MPLU_E_ARG;
     c->device = device;
     mplu_default_options(&c->opts);
-    CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-    if (gemm_tc_init() != 0) return MPLU_E_TMAP;
-    CKI(panel_init());
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    for (auto& e : c->ev) CK(cudaEventCreate(&e));
-    CK(cudaMalloc(&c->scales, SC_COUNT * sizeof(float)));
-    CK(cudaMalloc(&c->amax, sizeof(float)));
-    CK(cudaMalloc(&c->anorm, 2 * sizeof(double)));
-    CK(cudaMalloc(&c->norms, 2 * sizeof(double)));
-    CK(cudaMalloc(&c->status, sizeof(int)));
-    CK(cudaMalloc(&c->ready, sizeof(unsigned)));
+    auto init = [&]() -> int {
+        CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+        if (gemm_tc_init() != 0) return MPLU_E_TMAP;
+        CKI(panel_init());
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        for (auto& e : c->ev) CK(cudaEventCreate(&e));
+        CK(cudaMalloc(&c->scales, SC_COUNT * sizeof(float)));
+        CK(cudaMalloc(&c->amax, sizeof(float)));
+        CK(cudaMalloc(&c->anorm, 2 * sizeof(double)));
+        CK(cudaMalloc(&c->norms, 2 * sizeof(double)));
+        CK(cudaMalloc(&c->status, sizeof(int)));
+        CK(cudaMalloc(&c->ready, sizeof(unsigned)));
+        return 0;
+    };
+    const int rc = init();
+    if (rc) { mplu_destroy(c); return rc; }  // mplu_destroy copes with a partially built context
     *out = c;
     return 0;
 }
@@ -1166,7 +1183,7 @@ int mplu_create(mplu_context** out, int device) {
 void mplu_destroy(mplu_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     free_work(c);
     cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status); cudaFree(c->ready);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
@@ -1193,6 +1210,7 @@ int mplu_factor_device(mplu_context* c, int n, const double* dA, long long lda, 
     if (!c || !dA || n <= 0 || lda < n) return MPLU_E_ARG;
     CK(cudaSetDevice(c->device));
     if (opts) c->opts = *opts;
+    const OptionsScope scope(c);
     resolve_options(c, n);
     c->factored = false;
     c->allow_early = false;  // factor and solve are separate calls here: nothing could redo an early-scale overflow
@@ -1214,6 +1232,7 @@ int mplu_gesv_device(mplu_context* c, int n, const double* dA, long long lda, co
     if (!c || !dA || !db || !dx || n <= 0 || lda < n) return MPLU_E_ARG;
     CK(cudaSetDevice(c->device));
     if (opts) c->opts = *opts;
+    const OptionsScope scope(c);
     resolve_options(c, n);
     if (stats) memset(stats, 0, sizeof(*stats));
     c->factored = false;
@@ -1272,8 +1291,9 @@ int mplu_gesv_host(mplu_context* c, int n, const double* hA, long long lda, cons
     }
     cudaStream_t st = c->stream;
     if (opts) c->opts = *opts;
+    const OptionsScope scope(c);
+    const mplu_options used = c->opts;  // the request: the device path below resolves it again for itself
     resolve_options(c, n);
-    const mplu_options used = c->opts;
     CK(cudaEventRecord(c->ev[3], st));
     int rc;
     float h2d = 0.f;
@@ -1336,16 +1356,15 @@ int mplu_get_factors(mplu_context* c, double* LU, long long ldlu, int on_device)
         CK(cudaMalloc(&tmp, (size_t)n * n * sizeof(double)));
         dst = tmp;
     }
-    dim3 grid((n + 255) / 256, n);
+    dim3 grid((n + 255) / 256, n < 32768 ? n : 32768);  // gridDim.y <= 65535: columns on a grid-stride loop
     widen_kernel<<<grid, 256, 0, c->stream>>>(c->W, c->npad, n, dst, on_device ? ldlu : n);
-    CK(cudaGetLastError());
-    if (!on_device) {
-        CK(cudaMemcpy2DAsync(LU, (size_t)ldlu * sizeof(double), tmp, (size_t)n * sizeof(double),
-                             (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream));
-    }
-    CK(cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !on_device)
+        e = cudaMemcpy2DAsync(LU, (size_t)ldlu * sizeof(double), tmp, (size_t)n * sizeof(double),
+                              (size_t)n * sizeof(double), n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (tmp) cudaFree(tmp);
-    return 0;
+    return (int)e;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel hooks

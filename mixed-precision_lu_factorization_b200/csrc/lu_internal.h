@@ -74,7 +74,7 @@ struct mplu_context {
     static constexpr int kMaxSteps = 512;
     cudaEvent_t ev_step[4 * kMaxSteps] = {};  // per step: GETRF done, next-tile TRSM done, b2 done, b3a done
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { int n, npad, nb, precision, gemm_variant, max_sms, lookahead, side_sms, a_exp, l_exp, pdl, group, tile_ws; const void* W; const void* TW; int schedule; } gkey{};
+    std::vector<long long> gkey;  // what the cached graph was captured for (factor_impl)
     int g_gemm_launches = 0, g_kernel_launches = 0, g_trail_count = 0;
     double g_trail_flops = 0, g_trail_bytes = 0;
     bool capturing = false;

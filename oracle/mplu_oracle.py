@@ -17,7 +17,8 @@ Pinning status.  The reference ships NO golden vectors.  T
  (a) libc's real rand() (ctypes) for the generator, first 2x2 = 8.3 8.6 / 7.7 1.5           (tests/test_oracle.py)
  (b) host LAPACK dgetrf on column-dominant inputs: identity pivots, factors equal to 1e-12    (tests/test_oracle.py)
  (c) outputs of the UNMODIFIED reference built from /root/reference by oracle/Makefile and run on a B200 through
-     oracle/ref_driver.cu; fixtures under tests/golden/ (generated by oracle/make_golden.sh)  (tests/test_golden.py)
+     oracle/make_golden.py; fixtures under tests/golden/ (tests/test_oracle.py, tests/test_gpu_mpf.py), and LIVE in the
+     GPU tests through oracle/run_ref_mpf.py at n = 1024 / 4096 (tests/test_gpu_configs.py)
 The iterative-refinement part has no reference counterpart at all: for it "parity unpinned" applies and the
 comparator is host LAPACK dgetrs / dsgesv.
 """
@@ -129,6 +130,50 @@ def spd_kappa_matrix(n: int, kappa: float, seed: int = 1) -> np.ndarray:
     sigma = kappa ** (-np.arange(n) / max(n - 1, 1))
     H = np.eye(n) - 2.0 * np.outer(u, u)
     return (H * sigma) @ H
+
+
+def counter_matrix_into(out: np.ndarray, seed: int = 1, dominant: bool = True, block: int = 512) -> np.ndarray:
+    """counter_matrix(n, seed, dominant) written into the preallocated column-major n x n array `out` by column blocks
+    (bounded temporaries: the full-size n = 32768 input of bench.py's reference arm is 8 GiB).  Uses torch's threaded
+    CPU integer ops when torch is importable (same values bit for bit: tests/test_oracle.py), numpy otherwise."""
+    n = out.shape[0]
+    assert out.shape == (n, n) and out.dtype == np.float64 and out.flags.f_contiguous
+    try:
+        import torch
+    except ImportError:
+        torch = None
+    if torch is None:
+        i = np.arange(n, dtype=U64)[:, None]
+        for c0 in range(0, n, block):
+            c1 = min(n, c0 + block)
+            j = np.arange(c0, c1, dtype=U64)[None, :]
+            K = (splitmix64((U64(seed) << U64(40)) | (i << U64(20)) | j) % U64(100)).astype(np.int64)
+            blk = K.astype(np.float64) / 10.0
+            if dominant:
+                d = np.arange(c0, c1)
+                blk[d, d - c0] = (K.sum(axis=0) - K[d, d - c0]).astype(np.float64) / 10.0 + 1.0
+            out[:, c0:c1] = blk
+        return out
+
+    def lsr(v, k):  # logical shift right on int64 bit patterns
+        return (v >> k) & ((1 << (64 - k)) - 1)
+
+    outT = torch.from_numpy(out.T)  # C-contiguous: outT[c, r] = A[r, c]
+    i = torch.arange(n, dtype=torch.int64)[None, :]
+    for c0 in range(0, n, block):
+        c1 = min(n, c0 + block)
+        j = torch.arange(c0, c1, dtype=torch.int64)[:, None]
+        z = ((seed << 40) | (i << 20) | j) + (-7046029254386353131)   # + 0x9E3779B97F4A7C15 (mod 2^64)
+        z = (z ^ lsr(z, 30)) * (-4658895280553007687)                 # * 0xBF58476D1CE4E5B9
+        z = (z ^ lsr(z, 27)) * (-7723592293110705685)                 # * 0x94D049BB133111EB
+        z = z ^ lsr(z, 31)
+        K = ((lsr(z, 32) % 100) * (2 ** 32 % 100) + (z & 0xFFFFFFFF) % 100) % 100  # unsigned 64-bit value mod 100
+        blk = K.to(torch.float64) / 10.0
+        if dominant:
+            d = torch.arange(c0, c1)
+            blk[d - c0, d] = (K.sum(dim=1) - K[d - c0, d]).to(torch.float64) / 10.0 + 1.0
+        outT[c0:c1] = blk
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------------

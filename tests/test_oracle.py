@@ -107,3 +107,11 @@ def test_emulated_mixed_lu_refines_to_fp64(oracle):
         assert res["backward_error"] < 4 * n * 1.1e-16
         x_ref, _, _ = oracle.lapack_gesv(A, b)
         np.testing.assert_allclose(res["x"], x_ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,dominant", [(300, True), (1025, True), (1025, False)])
+def test_blocked_generator_equals_counter_matrix(oracle, n, dominant):
+    """bench.py's reference arm builds its full-size input by column blocks: same values bit for bit"""
+    A = np.empty((n, n), order="F")
+    oracle.counter_matrix_into(A, seed=3, dominant=dominant, block=256)
+    assert np.array_equal(A, oracle.counter_matrix(n, seed=3, dominant=dominant))

@@ -14,17 +14,7 @@ n = int(pos[0]) if pos else 16384
 s = m.Solver(0)
 
 
-def spd(n, kappa, seed=1):
-    g = torch.Generator(device="cuda").manual_seed(seed)
-    u = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
-    u /= u.norm()
-    sig = kappa ** (-torch.arange(n, dtype=torch.float64, device="cuda") / max(n - 1, 1))
-    du = sig * u
-    A = torch.diag(sig)
-    A -= 2.0 * torch.outer(u, du)
-    A -= 2.0 * torch.outer(du, u)
-    A += 4.0 * torch.dot(u, du) * torch.outer(u, u)
-    return A  # symmetric: row-major storage == column-major storage
+spd = m.generate_spd  # symmetric: row-major storage == column-major storage
 
 
 rows = []
