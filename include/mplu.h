@@ -81,6 +81,10 @@ typedef struct mplu_options {
                          solve is redone with the global scale.  Default 0: measured neutral (35.5 vs 35.9 ms and 37.1
                          vs 37.0 ms on two boxes) -- the bandwidth-bound cast slows the latency-bound tile as much as
                          the overlap saves */
+    int fuse_w;       /* GETRF of a diagonal block of at most fuse_w columns (multiple of 128) runs as ONE persistent launch
+                         (leaves + every product between them, grid barriers instead of kernel boundaries); same factors
+                         bit for bit.  Default 2048 (a whole diagonal tile); 0 = one launch per leaf / product group */
+    int fuse_ctas;    /* CTAs (= SMs) of that launch, even, default 16 */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -1,0 +1,64 @@
+// Fused GETRF of a diagonal block: ONE persistent launch runs the whole inverse-carrying recursion of lu.cu's
+// Sched::getrf -- the 128x128 leaves (leaf.cuh) and every tcgen05 product between them -- as a step program, with a
+// grid-wide barrier in global memory between dependent steps instead of a kernel boundary.  See getrf_fused.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mplu {
+
+// the 16-bit arrays a product can take its operands from (one TMA map each as A operand and as B operand)
+enum FusedMap : int { FM_WH = 0, FM_FH = 1, FM_LINV = 2, FM_UINV = 3, FM_T1 = 4, FM_T2 = 5, FM_COUNT = 6 };
+
+// out(m,n) = (accumulate ? C : 0) + alpha * sum_k A(m,k) B(k,n); same meaning as GemmParams (gemm_tc.h).
+// M, N multiples of 128, K a multiple of 64.
+struct alignas(16) FusedProblem {
+    int M, N, K;
+    int a_map, a_r0, a_c0;  // A block origin inside its parent array: (row m0, col k0)
+    int b_map, b_r0, b_c0;  // B block origin: (row k0, col n0)
+    int tri;                // GemmTri
+    int accumulate;
+    int h_rows, h_cols;     // the 16-bit copy is written where (m < h_rows || n < h_cols)
+    float alpha;            // times *alpha_p1 times *alpha_p2 (null = 1)
+    int ldc, ldh;
+    float* C;               // fp32 result (null: none)
+    void* H;                // 16-bit result scaled by *hscale_p (null: none)
+    const float* alpha_p1;
+    const float* alpha_p2;
+    const float* hscale_p;
+    long long pad_;
+};
+static_assert(sizeof(FusedProblem) == 112, "FusedProblem layout");
+
+enum FusedStepKind : int { FS_GEMM = 0, FS_LEAF = 1 };
+struct alignas(16) FusedStep {
+    int kind;
+    int first_problem, num_problems;  // FS_GEMM: up to 4 independent products
+    int tile_end[4];                  //          prefix sums of their 128x128 output tile counts
+    int k0, blk, first_in_tile, valid, T;  // FS_LEAF: block origin, 128-block index, first leaf of tile T?, valid rows
+};
+static_assert(sizeof(FusedStep) == 48, "FusedStep layout");
+
+struct alignas(64) FusedMaps {
+    CUtensorMap a[FM_COUNT];  // boxes of 64 (rows, contiguous) x 64
+    CUtensorMap b[FM_COUNT];  // boxes of 64 x 128
+};
+
+struct FusedArgs {
+    const void* program;  // device: num_steps FusedStep followed by num_problems FusedProblem
+    int num_steps, num_problems;
+    unsigned* barrier;    // device word, zero before the launch
+    float* W; long long ldw;
+    void* Linv16; void* Uinv16; long long ld16;  // band origins (row 0 of the tile's band, column 0 of the matrix)
+    float* Linv32; float* Uinv32;
+    float* inv_scales;
+    int bf16;
+    int* status;
+};
+
+int getrf_fused_init();  // per-device kernel attributes
+// grid of `num_ctas` (even, >= 2) CTAs in clusters of two, all of which must be able to be resident at the same time
+int launch_getrf_fused(const FusedMaps& maps, const FusedArgs& args, int num_ctas, cudaStream_t st);
+
+}  // namespace mplu

@@ -32,6 +32,9 @@ void free_work(mplu_context* c) {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     cudaFree(c->slab);
     cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
+    cudaFree(c->fprog_dev); cudaFree(c->fbar);
+    c->fprog_dev = nullptr; c->fprog_cap = 0; c->fbar = nullptr; c->fbar_cap = 0;
+    c->fprogs.clear(); c->fprog_host.clear(); c->fprog_key.clear(); c->fprog_uploaded = 0;
     c->slab = nullptr; c->slab_bytes = 0;
     c->W = nullptr; c->Wh = c->Fh = nullptr; c->Linv16 = c->Uinv16 = c->Tb1 = c->Tb2 = nullptr;
     c->Linv32 = c->Uinv32 = nullptr; c->cap_nb = 0;
@@ -89,6 +92,12 @@ int ensure_work(mplu_context* c, int n) {
         CK(cudaMalloc(&c->r, np * sizeof(double)));
         CK(cudaMalloc(&c->partial, (size_t)c->nchunk * np * sizeof(double)));
         CK(cudaMalloc(&c->y, 2 * np * sizeof(float)));
+        // fused GETRF: step programs (a leaf costs 48 bytes, a recursion node < 1.2 KiB) and one barrier word per launch
+        c->fprog_cap = (np / kDiagBlock) * 1536 + 65536;
+        CK(cudaMalloc(&c->fprog_dev, c->fprog_cap));
+        c->fbar_cap = (int)(np / kDiagBlock) + 16;
+        CK(cudaMalloc(&c->fbar, c->fbar_cap * sizeof(unsigned)));
+        CK(cudaMemset(c->fbar, 0, c->fbar_cap * sizeof(unsigned)));
         c->cap_npad = npad;
         c->cap_nb = NB;
     }
@@ -100,6 +109,8 @@ int ensure_work(mplu_context* c, int n) {
     CKI(make_operand(&c->opUinv, c->Uinv16, nbc, np, nbc));
     CKI(make_operand(&c->opT1, c->Tb1, nbc, nbc, nbc));
     CKI(make_operand(&c->opT2, c->Tb2, nbc, nbc, nbc));
+    const Operand16* ops[FM_COUNT] = {&c->opWh, &c->opFh, &c->opLinv, &c->opUinv, &c->opT1, &c->opT2};
+    for (int i = 0; i < FM_COUNT; ++i) { c->fmaps.a[i] = ops[i]->mapA; c->fmaps.b[i] = ops[i]->mapB2; }
     return 0;
 }
 
@@ -199,6 +210,12 @@ int traced_cast(mplu_context* c, int r0, int c0, int rows, int cols, cudaStream_
     return launch_shadow_cast(c->W + r0 + c0 * ld, ld, c->Wh + r0 + c0 * ld, ld, rows, cols, c->scales + SC_A,
                               c->opts.precision == MPLU_BF16, c->status, st);
 }
+// the fused GETRF launches of one factorization take their barrier words in order from a zeroed array
+int reset_fused_barriers(mplu_context* c, cudaStream_t st) {
+    c->fbar_next = 0;
+    if (c->fbar) CK(cudaMemsetAsync(c->fbar, 0, (size_t)c->fbar_cap * sizeof(unsigned), st));
+    return 0;
+}
 int traced_clear_bands(mplu_context* c, cudaStream_t st) {
     if (c->trace) {
         trace_push(c, TK_MEMSET, st, -1, -1, {{TA_LINV, 0, c->cap_nb, 0, c->npad, 1}, {TA_UINV, 0, c->cap_nb, 0, c->npad, 1}});
@@ -206,7 +223,7 @@ int traced_clear_bands(mplu_context* c, cudaStream_t st) {
     }
     CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * c->npad * sizeof(uint16_t), st));
     CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * c->npad * sizeof(uint16_t), st));
-    return 0;
+    return reset_fused_barriers(c, st);
 }
 
 // programmatic dependent launch: everywhere (opts.pdl == 1) or on the chain lane only (opts.pdl == 2)
@@ -245,8 +262,44 @@ int lane_sms(const mplu_context* c, const Lane& ln) {
     return sms;
 }
 
+// ---- fused GETRF: with c->rec set, the recursion records its products / leaves as steps of a program instead of
+// launching them (getrf_fused.cu interprets the program in one persistent launch)
+int fused_map_of(const mplu_context* c, const Operand16* o) {
+    if (o == &c->opWh) return FM_WH;
+    if (o == &c->opFh) return FM_FH;
+    if (o == &c->opLinv) return FM_LINV;
+    if (o == &c->opUinv) return FM_UINV;
+    if (o == &c->opT1) return FM_T1;
+    return FM_T2;
+}
+
+void rec_gemm_step(mplu_context* c, const GemmCall* calls, int count) {
+    FusedStep st{};
+    st.kind = FS_GEMM;
+    st.first_problem = (int)c->rec->problems.size();
+    int tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        const GemmCall& g = calls[i];
+        if (g.M <= 0 || g.N <= 0 || g.K <= 0) continue;
+        FusedProblem p{};
+        p.M = g.M; p.N = g.N; p.K = g.K;
+        p.a_map = fused_map_of(c, g.A); p.a_r0 = g.a_r0; p.a_c0 = g.a_c0;
+        p.b_map = fused_map_of(c, g.B); p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
+        p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
+        p.accumulate = g.accumulate ? 1 : 0;
+        p.h_rows = g.h_rows; p.h_cols = g.h_cols;
+        p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2; p.hscale_p = g.hscale_p;
+        p.C = g.C; p.ldc = (int)g.ldc; p.H = g.H; p.ldh = (int)g.ldh;
+        c->rec->problems.push_back(p);
+        tiles += (g.M / kDiagBlock) * (g.N / kDiagBlock);
+        st.tile_end[st.num_problems++] = tiles;
+    }
+    if (st.num_problems > 0) c->rec->steps.push_back(st);
+}
+
 int run_gemm(mplu_context* c, const Lane& ln, const GemmCall& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+    if (c->rec) { rec_gemm_step(c, &g, 1); return 0; }
     if (c->trace) { trace_gemm(c, ln, g, c->trace_group++); c->gemm_launches++; c->kernel_launches++; return 0; }
     const int variant = pick_variant(c, g);
     const bool cg2 = (variant == GEMM_CG2_AMN);
@@ -261,6 +314,7 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
     const bool e0 = g0.M <= 0 || g0.N <= 0 || g0.K <= 0, e1 = g1.M <= 0 || g1.N <= 0 || g1.K <= 0;
     if (e0) return e1 ? 0 : run_gemm(c, ln, g1);
     if (e1) return run_gemm(c, ln, g0);
+    if (c->rec && c->opts.group) { const GemmCall both[2] = {g0, g1}; rec_gemm_step(c, both, 2); return 0; }
     if (c->trace && c->opts.group && pick_variant(c, g0) == pick_variant(c, g1)) {  // one launch: the two are concurrent
         const int grp = c->trace_group++;
         trace_gemm(c, ln, g0, grp); trace_gemm(c, ln, g1, grp);
@@ -282,6 +336,7 @@ int run_gemm_pair(mplu_context* c, const Lane& ln, const GemmCall& g0, const Gem
 
 // Up to kMaxGroup independent products in ONE launch; falls back to separate launches when their tile variants differ.
 int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int count) {
+    if (c->rec && c->opts.group) { rec_gemm_step(c, calls, count); return 0; }
     GemmGroup g;
     g.count = 0;
     int variant = -1;
@@ -317,6 +372,17 @@ int run_gemm_group(mplu_context* c, const Lane& ln, const GemmCall* calls, int c
 }
 
 int mark(mplu_context* c, int tag, cudaStream_t st);
+
+// step programs recorded since the last upload -> device (pageable source: staged before the call returns)
+int upload_fused_programs(mplu_context* c, cudaStream_t st) {
+    const size_t have = c->fprog_host.size();
+    if (have > c->fprog_uploaded) {
+        CK(cudaMemcpyAsync(c->fprog_dev + c->fprog_uploaded, c->fprog_host.data() + c->fprog_uploaded, have - c->fprog_uploaded,
+                           cudaMemcpyHostToDevice, st));
+        c->fprog_uploaded = have;
+    }
+    return 0;
+}
 
 inline int split_width(int w) { return kDiagBlock * ((w / kDiagBlock + 1) / 2); }
 
@@ -365,9 +431,70 @@ struct Sched {
         return run_gemm_pair(c, ln, trsm_l_call(T, k0, w, lo, hi), trsm_u_call(T, k0, w, lo, hi));
     }
     // GETRF of the diagonal block [c0, c0+w)^2 inside tile T, leaving inv(L), inv(U) of the block in the bands.
+    // One persistent launch for the whole recursion below this block (getrf_fused.cu).
+    bool fuse(int w) const {
+        return !c->trace && !c->rec && c->opts.fuse_w > kDiagBlock && w > kDiagBlock && w <= c->opts.fuse_w &&
+               w % kDiagBlock == 0 && c->npad % kDiagBlock == 0;
+    }
+    int getrf_fused(const Lane& ln, int T, int c0, int w) const {
+        // programs depend on the geometry, the arrays and the options that shape the products
+        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip, c->opts.group,
+                                            (long long)reinterpret_cast<uintptr_t>(c->W)};
+        if (key != c->fprog_key) {
+            c->fprogs.clear(); c->fprog_host.clear(); c->fprog_uploaded = 0;
+            c->fprog_key = key;
+        }
+        const mplu_context::FusedProg* fp = nullptr;
+        for (const auto& f : c->fprogs) if (f.T == T && f.c0 == c0 && f.w == w) { fp = &f; break; }
+        if (!fp) {
+            mplu_context::FusedRecorder r;
+            c->rec = &r;
+            const int rc = getrf(ln, T, c0, w);
+            c->rec = nullptr;
+            if (rc) return rc;
+            const size_t sb = r.steps.size() * sizeof(FusedStep), pb = r.problems.size() * sizeof(FusedProblem);
+            const size_t off = c->fprog_host.size();
+            if (off + sb + pb > c->fprog_cap) return MPLU_E_ARG;
+            c->fprog_host.resize(off + sb + pb);
+            memcpy(c->fprog_host.data() + off, r.steps.data(), sb);
+            memcpy(c->fprog_host.data() + off + sb, r.problems.data(), pb);
+            c->fprogs.push_back({T, c0, w, off, (int)r.steps.size(), (int)r.problems.size()});
+            fp = &c->fprogs.back();
+        }
+        // new programs reach the device before the launch: here when launching directly, after the capture otherwise
+        if (!c->capturing) CKI(upload_fused_programs(c, ln.st));
+        if (c->fbar_next >= c->fbar_cap) return MPLU_E_ARG;
+        FusedArgs a{};
+        a.program = c->fprog_dev + fp->offset;
+        a.num_steps = fp->num_steps; a.num_problems = fp->num_problems;
+        a.barrier = c->fbar + c->fbar_next++;
+        a.W = c->W; a.ldw = ld;
+        a.Linv16 = c->Linv16; a.Uinv16 = c->Uinv16; a.ld16 = ldi;
+        a.Linv32 = c->Linv32; a.Uinv32 = c->Uinv32;
+        a.inv_scales = c->inv_scales;
+        a.bf16 = c->opts.precision == MPLU_BF16;
+        a.status = c->status;
+        int G = c->opts.fuse_ctas > 0 ? c->opts.fuse_ctas : 16;
+        const int budget = lane_sms(c, ln);
+        if (G > budget) G = budget;
+        G -= G % 2;
+        if (G < 2) G = 2;
+        c->gemm_launches++;
+        c->kernel_launches++;
+        return launch_getrf_fused(c->fmaps, a, G, ln.st);
+    }
     int getrf(const Lane& ln, int T, int c0, int w) const {
+        if (fuse(w)) return getrf_fused(ln, T, c0, w);
         if (w <= kDiagBlock) {
             const int blk = c0 / kDiagBlock;
+            if (c->rec) {
+                FusedStep st{};
+                st.kind = FS_LEAF;
+                st.k0 = c0; st.blk = blk; st.first_in_tile = c0 == T; st.T = T;
+                st.valid = c->n - c0 < kDiagBlock ? c->n - c0 : kDiagBlock;
+                c->rec->steps.push_back(st);
+                return 0;
+            }
             uint16_t* l16 = c->Linv16 + (c0 - T) + (long long)c0 * ldi;
             uint16_t* u16 = c->Uinv16 + (c0 - T) + (long long)c0 * ldi;
             if (c->trace) {  // reads and rewrites its W block, writes its triangles of the two inverse bands
@@ -416,6 +543,7 @@ int getrf_resident_tile(mplu_context* c, cudaStream_t st, int w) {
     CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, w, w, c->scales + SC_A, bf16, c->status, st));
     CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * w * sizeof(uint16_t), st));
     CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * w * sizeof(uint16_t), st));
+    CKI(reset_fused_barriers(c, st));
     const Sched S{c, ld, (long long)c->cap_nb};
     return S.getrf(ln, 0, 0, w);
 }
@@ -849,6 +977,7 @@ int prologue_left(mplu_context* c, const double* dA, long long lda) {
     CKI(launch_shadow_cast(c->W, ld, c->Wh, ld, npad, NB, c->scales + SC_A, bf16, c->status, st));
     CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
     CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CKI(reset_fused_barriers(c, st));
     c->kernel_launches += 3;
     CK(cudaEventRecord(c->ev_pro[0], st));
     CK(cudaStreamWaitEvent(c->side, c->ev_pro[0], 0));
@@ -908,7 +1037,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, (long long)early, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, (long long)early, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
@@ -938,6 +1067,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
         }
     }
     if (use_graph) {
+        CKI(upload_fused_programs(c, st));  // programs recorded during the capture (no-op on a cache hit)
         c->gemm_launches = c->g_gemm_launches; c->kernel_launches = c->g_kernel_launches;
         c->trail_count = c->g_trail_count; c->trail_flops = c->g_trail_flops; c->trail_bytes = c->g_trail_bytes;
         CK(cudaGraphLaunch(c->graph_exec, st));
@@ -980,6 +1110,7 @@ int factor_streamed(mplu_context* c, int n, const double* hA, long long lda, dou
     CK(cudaMemsetAsync(c->amax, 0, sizeof(float), st));
     CK(cudaMemsetAsync(c->Linv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
     CK(cudaMemsetAsync(c->Uinv16, 0, (size_t)c->cap_nb * npad * sizeof(uint16_t), st));
+    CKI(reset_fused_barriers(c, st));
     c->gemm_launches = 0;
     c->kernel_launches = 0;
     c->trail_count = 0;
@@ -1144,6 +1275,8 @@ void mplu_default_options(mplu_options* o) {
     o->eager = 1;
     o->stream_c = 1;
     o->early_scale = 0;
+    o->fuse_w = 2048;
+    o->fuse_ctas = 16;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -1160,6 +1293,7 @@ int mplu_create(mplu_context** out, int device) {
         CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
         if (gemm_tc_init() != 0) return MPLU_E_TMAP;
         CKI(panel_init());
+        CKI(getrf_fused_init());
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));

@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/mplu.h"
 #include "gemm_tc.h"
+#include "getrf_fused.h"
 #include "kernels.h"
 
 #include <vector>
@@ -61,6 +62,19 @@ struct mplu_context {
     // dry run: non-null = record the schedule instead of launching it
     std::vector<TraceOp>* trace = nullptr;
     int trace_group = 0;
+    // fused GETRF (getrf_fused.cu): step programs of the diagonal blocks, recorded once per (geometry, options) by running
+    // the recursion with `rec` set, kept on the device; one barrier word per fused launch of a factorization
+    struct FusedProg { int T, c0, w; size_t offset; int num_steps, num_problems; };
+    struct FusedRecorder { std::vector<mplu::FusedStep> steps; std::vector<mplu::FusedProblem> problems; };
+    std::vector<FusedProg> fprogs;
+    std::vector<unsigned char> fprog_host;
+    std::vector<long long> fprog_key;
+    unsigned char* fprog_dev = nullptr;
+    size_t fprog_cap = 0, fprog_uploaded = 0;
+    FusedRecorder* rec = nullptr;
+    unsigned* fbar = nullptr;
+    int fbar_cap = 0, fbar_next = 0;
+    mplu::FusedMaps fmaps;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {
         uint16_t* base = nullptr;

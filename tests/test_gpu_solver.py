@@ -313,7 +313,8 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
     s = mplu.Solver(0)
     try:
         common = (dict(), dict(group=0), dict(tri_skip=0), dict(lookahead=0), dict(use_graph=0), dict(gemm_variant=mplu.GEMM_CG2),
-                  dict(stream_c=0))
+                  dict(stream_c=0), dict(fuse_w=0), dict(fuse_w=0, group=0), dict(fuse_w=256), dict(fuse_w=256, fuse_ctas=2),
+                  dict(fuse_w=512, fuse_ctas=8, use_graph=0), dict(fuse_w=512, fuse_ctas=32, tri_skip=0))
         right = tuple(dict(schedule=0, **kw) for kw in common) + (
             dict(schedule=0, tile_ws=1), dict(schedule=0, side_sms=16, side_sms_early=8), dict(schedule=0, pdl=2))
         left = tuple(dict(schedule=1, **kw) for kw in common) + (
@@ -327,5 +328,29 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
                 ref = LU.clone()
             else:
                 assert torch.equal(LU, ref), kw
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("n,nb,fuse_w,ctas", [(4096, 2048, 2048, 16), (4096, 2048, 1024, 8), (4096, 4096, 4096, 16), (3000, 1024, 1024, 4)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_fused_getrf_gives_bit_identical_factors(mplu, oracle, n, nb, fuse_w, ctas, precision):
+    """opts.fuse_w: the GETRF of a diagonal block (leaves + every product between them) as ONE persistent launch with grid
+    barriers between the steps (csrc/getrf_fused.cu) instead of one launch per leaf / product group.  Same products on the
+    same operands in the same order: factors, iteration counts and solutions are bit-identical.  nb = 4096 exercises the
+    step program read from global memory (it does not fit the shared-memory staging area), n = 3000 the identity padding."""
+    import torch
+    A, b = mplu.generate(n, seed=6)
+    s = mplu.Solver(0)
+    try:
+        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=0, precision=precision))
+        LU0 = s.factors(n).clone()
+        for rep in range(2):  # second pass replays the cached graph / programs
+            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=fuse_w, fuse_ctas=ctas, precision=precision))
+            assert st1.converged == 1 and st1.status_bits == 0 and st1.iters == st0.iters
+            assert st1.kernel_launches < st0.kernel_launches
+            assert torch.equal(s.factors(n), LU0)
+            assert torch.equal(x1, x0)
+        assert float((x1 - 1).abs().max()) < 1e-11
     finally:
         s.close()
