@@ -146,9 +146,21 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
     float mx = 0.f;                 // largest scaled fp16 magnitude written (overflow detection)
     const uint32_t idesc = make_idesc_f16(FBM, FBN, a.bf16 != 0, true, false);
 
+    // development aid (mplu_debug_fused_profile): CTA 0 stamps clock64 at the head of every step and at the end,
+    // followed by %globaltimer (ns) at both ends of the launch for calibration
+    auto stamp = [&](int slot, bool wall) {
+        if (a.dbg_clk && cta == 0 && tid == 0) {
+            long long t_;
+            if (wall) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) :: "memory");
+            else asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory");
+            a.dbg_clk[slot] = t_;
+        }
+    };
+    stamp(a.num_steps + 1, true);
 #pragma unroll 1
     for (int s = 0; s < a.num_steps; ++s) {
         const FusedStep st = steps[s];
+        stamp(s, false);
         if (st.kind == FS_LEAF) {
             if (cta < 2) {
                 const long long off16 = (long long)(st.k0 - st.T) + (long long)st.k0 * a.ld16;
@@ -283,6 +295,8 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
         }
         grid_step_barrier(a.barrier, (unsigned)G * (unsigned)(s + 1));
     }
+    stamp(a.num_steps, false);
+    stamp(a.num_steps + 2, true);
     if (warp < F_EPI_WARPS) {
         const float hmax = a.bf16 ? 3.0e38f : 65504.f;
         if (a.status && __any_sync(0xffffffffu, mx > hmax) && lane == 0) atomicOr(a.status, 1);

@@ -55,6 +55,7 @@ struct FusedArgs {
     float* inv_scales;
     int bf16;
     int* status;
+    long long* dbg_clk;  // development aid: num_steps + 3 time stamps (null: none)
 };
 
 int getrf_fused_init();  // per-device kernel attributes

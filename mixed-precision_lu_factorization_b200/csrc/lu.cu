@@ -32,7 +32,8 @@ void free_work(mplu_context* c) {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     cudaFree(c->slab);
     cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
-    cudaFree(c->fprog_dev); cudaFree(c->fbar);
+    cudaFree(c->fprog_dev); cudaFree(c->fbar); cudaFree(c->fprof);
+    c->fprof = nullptr;
     c->fprog_dev = nullptr; c->fprog_cap = 0; c->fbar = nullptr; c->fbar_cap = 0;
     c->fprogs.clear(); c->fprog_host.clear(); c->fprog_key.clear(); c->fprog_uploaded = 0;
     c->slab = nullptr; c->slab_bytes = 0;
@@ -474,6 +475,12 @@ struct Sched {
         a.inv_scales = c->inv_scales;
         a.bf16 = c->opts.precision == MPLU_BF16;
         a.status = c->status;
+        if (c->fprof_on && c->fprof && fp->num_steps + 3 <= mplu_context::kFusedProfSlots) {
+            const int li = (int)(a.barrier - c->fbar);
+            a.dbg_clk = c->fprof + (size_t)li * mplu_context::kFusedProfSlots;
+            if ((int)c->fprof_prog.size() <= li) c->fprof_prog.resize(li + 1, -1);
+            c->fprof_prog[li] = (int)(fp - c->fprogs.data());
+        }
         int G = c->opts.fuse_ctas > 0 ? c->opts.fuse_ctas : 16;
         const int budget = lane_sms(c, ln);
         if (G > budget) G = budget;
@@ -561,6 +568,7 @@ int getrf_in_workspace(mplu_context* c, const Lane& ln, int T, int w) {
     t->opts.precision = c->opts.precision;
     int* own_status = t->status;
     t->status = c->status;  // the tile's kernels report into the caller's status word
+    t->capturing = c->capturing;  // fused step programs recorded during a capture are uploaded after it (factor_impl)
     CK(cudaMemcpy2DAsync(t->W, (size_t)tld * sizeof(float), c->W + T + (long long)T * ld, (size_t)ld * sizeof(float),
                          wb * sizeof(float), wb, cudaMemcpyDeviceToDevice, st));
     t->gemm_launches = t->kernel_launches = 0;
@@ -1068,6 +1076,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     }
     if (use_graph) {
         CKI(upload_fused_programs(c, st));  // programs recorded during the capture (no-op on a cache hit)
+        if (c->tile) CKI(upload_fused_programs(c->tile, st));
         c->gemm_launches = c->g_gemm_launches; c->kernel_launches = c->g_kernel_launches;
         c->trail_count = c->g_trail_count; c->trail_flops = c->g_trail_flops; c->trail_bytes = c->g_trail_bytes;
         CK(cudaGraphLaunch(c->graph_exec, st));
@@ -1682,6 +1691,46 @@ int mplu_debug_timeline(mplu_context* c, int* tags, float* ms, int max) {
         cudaEventElapsedTime(&ms[i], c->mark_ev[0], c->mark_ev[i]);
     }
     return n;
+}
+
+// development aid: per-step time stamps of the fused GETRF launches.  enable: takes effect at the next schedule capture.
+// mplu_debug_fused_profile: for fused launch `launch` of the last factorization writes, per step, (kind, tiles, K of the
+// first product | leaf origin, clock64 at the step's head) as 4 long longs, then one record (-1, 0, ns of the whole
+// launch by %globaltimer, clock64 at the end).  Returns the number of records, 0 if that launch was not profiled.
+int mplu_debug_fused_profile_enable(mplu_context* c, int on) {
+    if (!c) return MPLU_E_ARG;
+    CK(cudaSetDevice(c->device));
+    c->fprof_on = on != 0;
+    if (c->fprof_on && !c->fprof && c->fbar_cap > 0)
+        CK(cudaMalloc(&c->fprof, (size_t)c->fbar_cap * mplu_context::kFusedProfSlots * sizeof(long long)));
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return 0;
+}
+int mplu_debug_fused_profile(mplu_context* c, int launch, long long* out, int max_records) {
+    if (!c || !out || !c->fprof || launch < 0 || launch >= (int)c->fprof_prog.size() || c->fprof_prog[launch] < 0) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    const mplu_context::FusedProg& fp = c->fprogs[c->fprof_prog[launch]];
+    std::vector<long long> clk(mplu_context::kFusedProfSlots);
+    if (cudaMemcpy(clk.data(), c->fprof + (size_t)launch * mplu_context::kFusedProfSlots, clk.size() * sizeof(long long),
+                   cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    const FusedStep* steps = reinterpret_cast<const FusedStep*>(c->fprog_host.data() + fp.offset);
+    const FusedProblem* probs = reinterpret_cast<const FusedProblem*>(c->fprog_host.data() + fp.offset + fp.num_steps * sizeof(FusedStep));
+    int nrec = 0;
+    for (int s = 0; s < fp.num_steps && nrec < max_records; ++s, ++nrec) {
+        const FusedStep& st = steps[s];
+        out[4 * nrec] = st.kind;
+        out[4 * nrec + 1] = st.kind == FS_GEMM ? st.tile_end[st.num_problems - 1] : 1;
+        out[4 * nrec + 2] = st.kind == FS_GEMM ? probs[st.first_problem].K : st.k0;
+        out[4 * nrec + 3] = clk[s];
+    }
+    if (nrec < max_records) {
+        out[4 * nrec] = -1; out[4 * nrec + 1] = 0;
+        out[4 * nrec + 2] = clk[fp.num_steps + 2] - clk[fp.num_steps + 1];
+        out[4 * nrec + 3] = clk[fp.num_steps];
+        ++nrec;
+    }
+    return nrec;
 }
 
 int mplu_residual(int n, const double* dA, long long lda, const double* dx, const double* db, double* dr,

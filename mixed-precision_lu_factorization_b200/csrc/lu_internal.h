@@ -74,6 +74,12 @@ struct mplu_context {
     FusedRecorder* rec = nullptr;
     unsigned* fbar = nullptr;
     int fbar_cap = 0, fbar_next = 0;
+    // development aid (mplu_debug_fused_profile): per fused launch of the last factorization, which program it ran and
+    // a slice of kFusedProfSlots time stamps
+    static constexpr int kFusedProfSlots = 256;
+    long long* fprof = nullptr;
+    bool fprof_on = false;
+    std::vector<int> fprof_prog;  // launch index -> index into fprogs
     mplu::FusedMaps fmaps;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {

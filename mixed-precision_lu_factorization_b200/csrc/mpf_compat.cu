@@ -21,9 +21,12 @@
 namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------------------------
-// fp16 panel LU with partial pivoting.  Arg-max of |a| over rows j.. with "first maximum wins" (the reference's two
-// strict-'>' reductions, hgetf2_kernel.cu:50,74) is one 64-bit atomicMax per block on the key
-//   (bits of |a| as fp16) << 32 | (0xFFFFFFFF - row)        -- larger value first, then smaller row.
+// fp16 panel LU with partial pivoting.  Arg-max of |a| over rows j..: among EQUAL maxima the reference keeps the lower
+// slot at every merge of its 256-slot shared-memory tree (strict '>', hgetf2_kernel.cu:48-56) and the lower block in
+// its scan over the blocks (:72-79), so the winner is the tied row with the smallest
+//   order(row) = ((row - j) / 256) << 8 | bitreverse8((row - j) % 256)
+// (not the first row: found by the live-reference parity test on a tie-rich input).  Here that is one 64-bit atomicMax
+// per block on the key   (bits of |a| as fp16) << 32 | (0xFFFFFFFF - order(row)).
 // Like the reference's g_block_max_* scratch (hgetf2_kernel.cu:6-7) the key slots are __device__ globals, so two
 // concurrent launches on one device must not overlap (same restriction as the reference).
 __device__ unsigned long long g_hgetf2_key[2];
@@ -43,7 +46,9 @@ __global__ void HGETF2_kernel(fp16 *panel, int ld, int rows, int cols, int *ipiv
         unsigned long long best = 0ull;
         for (long long r = j + gtid; r < rows; r += gsz) {
             const unsigned short bits = __half_as_ushort(__habs(panel[(long long)j * ld + r]));
-            const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+            const unsigned rel = (unsigned)(r - j);
+            const unsigned order = (rel & ~255u) | (__brev(rel & 255u) >> 24);
+            const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned long long)(0xFFFFFFFFu - order);
             best = key > best ? key : best;
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -63,7 +68,8 @@ __global__ void HGETF2_kernel(fp16 *panel, int ld, int rows, int cols, int *ipiv
         grid.sync();
         const unsigned long long win = *reinterpret_cast<volatile unsigned long long*>(slot);
         // all-zero (or empty) column: the reference's scan keeps its initial index j (hgetf2_kernel.cu:35,69)
-        const int piv = ((win >> 32) == 0ull) ? j : (int)(0xFFFFFFFFu - (unsigned)(win & 0xFFFFFFFFull));
+        const unsigned word = 0xFFFFFFFFu - (unsigned)(win & 0xFFFFFFFFull);  // order(row) of the winner
+        const int piv = ((win >> 32) == 0ull) ? j : j + (int)((word & ~255u) | (__brev(word & 255u) >> 24));
         if (gtid == 0) {
             ipiv_panel[j] = piv + 1;
             g_hgetf2_key[(j + 1) & 1] = 0ull;  // the other slot is idle during this column: clear it for column j+1

@@ -193,10 +193,25 @@ def _h(x64):
         return np.asarray(x64, dtype=np.float64).astype(np.float16)
 
 
+def _hgetf2_tie_order(nmax: int = 1 << 20) -> np.ndarray:
+    """rank of row offset rel = row - j in the reference's tie-break: (rel // 256, bitreverse8(rel % 256))"""
+    rel = np.arange(nmax, dtype=np.int64)
+    t = rel & 255
+    rev = np.zeros_like(t)
+    for b in range(8):
+        rev |= ((t >> b) & 1) << (7 - b)
+    return ((rel >> 8) << 8) | rev
+
+
+_HGETF2_TIE_ORDER = _hgetf2_tie_order()
+
+
 def hgetf2(panel: np.ndarray, fused: bool = True):
     """fp16 partial-pivot LU of a rows x cols panel (hgetf2_kernel.cu:22-119).  Returns (panel_out, ipiv) with
-    ipiv 1-based panel-local.  Pivot = first row attaining max |a| over rows j.. (strict '>' in both reductions,
-    :50,:74; NaN never wins).  Multiplier = fp16 division; update a -= m*b either fused (one rounding: what -O3
+    ipiv 1-based panel-local.  Pivot = a row attaining max |a| over rows j..; among EQUAL maxima the reference's
+    reductions (strict '>' in the 256-slot shared-memory tree, :48-56, then a linear scan over the blocks, :72-79) keep
+    the lower slot at every merge, i.e. the winner is the tied row with the smallest (block, bit-reversed thread index)
+    -- not the first row (found by the live-reference parity test on a tie-rich input).  NaN never wins.  Multiplier = fp16 division; update a -= m*b either fused (one rounding: what -O3
     emits) or as two rounded fp16 operations (the reference's own -O0 build)."""
     P = np.array(panel, dtype=np.float16, copy=True)
     rows, cols = P.shape
@@ -207,7 +222,10 @@ def hgetf2(panel: np.ndarray, fused: bool = True):
             continue
         col = np.abs(P[j:, j].astype(np.float32))
         col = np.where(np.isnan(col), np.float32(-1), col)
-        p = int(np.argmax(col)) + j if col.size and col.max() > 0 else j
+        p = j
+        if col.size and col.max() > 0:
+            tied = np.flatnonzero(col == col.max())
+            p = int(tied[np.argmin(_HGETF2_TIE_ORDER[tied])]) + j
         ipiv[j] = p + 1
         if p != j:
             P[[j, p], :] = P[[p, j], :]

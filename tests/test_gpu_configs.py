@@ -73,20 +73,19 @@ def test_live_reference_parity(mplu, oracle, solver, tmp_path, n):
 @pytest.mark.skipif(not os.path.exists(REF_LIB), reason="oracle/_ref not built")
 @pytest.mark.parametrize("n", [128, 512])
 def test_live_reference_parity_pivoting_input(mplu, oracle, tmp_path, n):
-    """A non-dominant input makes the reference's fp16 pivot discovery (MPF.cu:125-163) choose real row swaps.  At
-    n = 128 the drop-in MPF() must return the same pivot vector and fp64-equal factors; at n = 512 fp16 near-ties make
-    the sequence depend on the last bit of the fp16 division (tests/test_oracle.py), so there both
-    outputs must pass the reference's own P*L*U == A check (benchmark.cpp:97-144)."""
+    """A non-dominant input makes the reference's fp16 pivot discovery (MPF.cu:125-163) choose real row swaps, and its
+    value set (k/10) is rich in exact fp16 ties, which the reference breaks by the shape of its reduction tree
+    (hgetf2_kernel.cu:48-56,72-79): the drop-in MPF() must return the same pivot vector and fp64-equal factors."""
     g = _run_reference(tmp_path, n, seed=7, kind="rand")
     A = oracle.counter_matrix(n, seed=7, dominant=False)
     LU = np.asfortranarray(A.copy())
     ip = mplu.MPF(LU, 32)
     assert (g["ipiv"] != np.arange(1, n + 1)).sum() > n // 2
     assert oracle.check_correctitude(A, g["LU"], g["ipiv"], tol=1e-9)
-    assert oracle.check_correctitude(A, LU, ip, tol=1e-9)
-    if n <= 128 or np.array_equal(ip, g["ipiv"]):
-        assert np.array_equal(ip, g["ipiv"])
-        np.testing.assert_allclose(LU, g["LU"], rtol=0, atol=1e-10 * np.abs(g["LU"]).max())
+    assert np.array_equal(ip, g["ipiv"])
+    np.testing.assert_allclose(LU, g["LU"], rtol=0, atol=1e-10 * np.abs(g["LU"]).max())
+    o_lu, o_ip = oracle.mpf_reference(A, 32)  # and the CPU restatement agrees with the live reference
+    assert np.array_equal(o_ip, g["ipiv"])
 
 
 # ---- configs[4]: condition-number sweep at n = 16384 --------------------------------------------------------------------

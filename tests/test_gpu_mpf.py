@@ -28,7 +28,7 @@ def test_mpf_dominant_vs_golden(mplu, oracle, n):
     assert oracle.check_correctitude(A, LU, ipiv)  # the reference's own 1e-10 check (benchmark.cpp:97-144)
 
 
-@pytest.mark.parametrize("n", [64, 128])
+@pytest.mark.parametrize("n", [64, 128, 256])
 def test_mpf_pivoting_vs_golden(mplu, oracle, n):
     g = np.load(os.path.join(GOLDEN, f"ref_mpf_rand_n{n}.npz"))
     A = _stream_matrix(oracle, n)

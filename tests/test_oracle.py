@@ -86,14 +86,31 @@ def test_golden_random_pivoting_vs_oracle(oracle, n):
     assert oracle.check_correctitude(A, g["LU"], g["ipiv"])
 
 
-def test_golden_random_256_is_valid_factorization(oracle):
-    # at n=256 fp16 near-ties make the pivot sequence depend on the fp16 division's last bit; both the
-    # reference's and the oracle's factorizations must still satisfy the reference's own check
+def test_golden_random_256_matches_with_the_references_tie_break(oracle):
+    # Exact ties of |a| in fp16 are frequent on this value set (k/10); the reference's reduction tree does NOT keep the
+    # first maximum but the tied row with the smallest (block, bit-reversed thread index) -- hgetf2_kernel.cu:48-56,72-79.
+    # With that rule restated the n = 256 golden output (which "first maximum wins" missed) is reproduced exactly.
     g = np.load(os.path.join(GOLDEN, "ref_mpf_rand_n256.npz"))
     A = _stream_matrix(oracle, 256)
     assert oracle.check_correctitude(A, g["LU"], g["ipiv"])
     LU, ipiv = oracle.mpf_reference(A, 32)
-    assert oracle.check_correctitude(A, LU, ipiv)
+    assert np.array_equal(ipiv, g["ipiv"])
+    np.testing.assert_allclose(g["LU"], LU, rtol=0, atol=1e-11 * np.abs(LU).max())
+
+
+def test_hgetf2_tie_break_is_the_reduction_trees(oracle):
+    # column with its maximum at rows 20 and 68: slot 68 % 64 = 4 absorbs row 68 first and later wins the tie against
+    # slot 20 (strict '>'), so the pivot is row 68 although row 20 comes first
+    P = np.zeros((128, 1), dtype=np.float16)
+    P[20, 0] = P[68, 0] = 9.9
+    P[5, 0] = 3.0
+    _, ip = oracle.hgetf2(P)
+    assert ip[0] == 69
+    # across blocks of 256 rows the lower block wins
+    P = np.zeros((600, 1), dtype=np.float16)
+    P[300, 0] = P[255, 0] = 2.5
+    _, ip = oracle.hgetf2(P)
+    assert ip[0] == 256
 
 
 def test_emulated_mixed_lu_refines_to_fp64(oracle):
