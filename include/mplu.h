@@ -85,6 +85,11 @@ typedef struct mplu_options {
                          (leaves + every product between them, grid barriers instead of kernel boundaries); same factors
                          bit for bit.  Default 2048 (a whole diagonal tile); 0 = one launch per leaf / product group */
     int fuse_ctas;    /* CTAs (= SMs) of that launch, even, default 16 */
+    int lazy_touch;   /* MPLU_SCHED_LEFT, n a multiple of 128: 1 (default) = no separate fp64 -> fp32 cast pass over A.  Only the
+                         first block column / block row are cast up front (the fp16 scale comes from them); every other
+                         tile's first Schur update takes its addend straight from the caller's fp64 matrix (the cast is fused
+                         into the GEMM epilogue's loads) and ||A||_inf is formed by the first residual pass.  An entry that
+                         leaves the fp16 range under that scale is detected and the factorization redone the eager way */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -69,6 +69,17 @@ __device__ __forceinline__ void epi_load(float (&dst)[32], const GemmParams& p, 
     }
 }
 
+// addend of a tile's first update: the original fp64 matrix, cast on the fly (aligned path only: the host uses it for
+// matrices whose order is a multiple of 128)
+template <bool kStream>
+__device__ __forceinline__ void epi_load64(float (&dst)[32], const GemmParams& p, const ARef& ar, int row, int col0, bool ok) {
+    if (ok) {
+        const double* src = ar.A + (p.cin64_r0 + row) + (long long)(p.cin64_c0 + col0) * ar.lda;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = static_cast<float>(kStream ? __ldcs(src + (long long)j * ar.lda) : src[(long long)j * ar.lda]);
+    }
+}
+
 template <bool kRagged, bool kStream>
 __device__ __forceinline__ void epi_store(const uint32_t (&v)[32], const float (&cin)[32], const GemmParams& p,
                                           float alpha, float hs, int row, int col0, bool ok, float& mx) {
@@ -303,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         bool cur_ok = false;
         const GemmParams* lp = &p0;                 // problem of the chunk being loaded / finished
         const GemmParams* cp = &p0;
+        ARef l_aref{nullptr, 0};
         float l_alpha = 0.f, l_hs = 0.f, c_alpha = 0.f, c_hs = 0.f;
 #pragma unroll 1
         for (int i = 0; i <= nchunks; ++i) {
@@ -322,6 +334,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                     if (lp->alpha_p2) l_alpha *= __ldg(lp->alpha_p2);
                     l_hs = lp->hscale;
                     if (lp->hscale_p) l_hs *= __ldg(lp->hscale_p);
+                    if (lp->cin64) l_aref = *lp->cin64;
                 }
                 nx_col0 = t_colbase + (i & 3) * 32;
                 nx_ok = (t_row0 < lp->M) && (nx_col0 < lp->N);
@@ -339,6 +352,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
             if (i < nchunks) {
                 if (lp->Cin != nullptr) {
                     epi_load<kRagged, kStream>(cin_nxt, *lp, t_row0 + lane, nx_col0, nx_ok);
+                } else if (!kRagged && lp->cin64 != nullptr) {
+                    epi_load64<kStream>(cin_nxt, *lp, l_aref, t_row0 + lane, nx_col0, nx_ok);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) cin_nxt[j] = 0.f;
@@ -455,6 +470,20 @@ int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return (int)r;
+}
+
+int make_tmap_plain(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols) {
+    EncodeFn enc = get_encode_fn();
+    if (!enc || (elem_bytes != 2 && elem_bytes != 4)) return -1;
+    cuuint64_t dims[2] = {rows, cols};
+    cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {box_rows, box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return (int)r;
 }
 

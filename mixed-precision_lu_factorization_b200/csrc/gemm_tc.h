@@ -22,6 +22,14 @@ enum GemmVariant : int {
     GEMM_CG2_AK = 3,   // CTA-pair, same A layout; for these two (a_r0,a_c0) = (k0, m0) in the transposed parent
 };
 
+// Where the caller's ORIGINAL fp64 matrix lives (device memory, written before every factorization): lets a captured
+// schedule take the addend of a tile's FIRST update straight from A -- the fp64 -> fp32 cast fused into the update's
+// loads (reference: the cast pass of /root/reference/MPF.cu:20-25,106-121) -- without baking A's address into the graph.
+struct ARef {
+    const double* A;
+    long long lda;
+};
+
 struct GemmParams {
     int M, N, K;
     int a_r0, a_c0;  // origin of the A block inside its parent array: (row m0, col k0)
@@ -30,6 +38,8 @@ struct GemmParams {
     long long ldc;
     const float* Cin;  // fp32 addend (may alias C; null = none)
     long long ldcin;
+    const ARef* cin64;  // instead of Cin: addend = (float)A(cin64_r0 + m, cin64_c0 + n) of the original fp64 matrix
+    int cin64_r0, cin64_c0;
     void* H;  // optional 16-bit shadow of the output, column-major, offset to the block origin
     long long ldh;
     int h_rows, h_cols;     // shadow is written where (m < h_rows || n < h_cols)
@@ -50,6 +60,10 @@ struct GemmParams {
 // elements and leading dimension `ld`; a box is box_rows (contiguous) x box_cols.
 int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                     uint32_t box_cols);
+
+// The same without swizzle, 2- or 4-byte elements (shared -> global tile stores: the tile sits densely in shared memory).
+int make_tmap_plain(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols);
 
 // Box shapes each variant expects for its A and B maps.
 void gemm_box_shapes(int variant, uint32_t* a_box_rows, uint32_t* a_box_cols, uint32_t* b_box_rows,

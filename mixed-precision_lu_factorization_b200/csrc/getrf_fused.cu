@@ -18,7 +18,7 @@
 #include "getrf_fused.h"
 
 #include "gemm_tc.h"
-#include "leaf.cuh"
+#include "leaf_tc.cuh"
 #include "ptx.cuh"
 
 #include <cuda_bf16.h>
@@ -29,11 +29,13 @@ namespace mplu {
 namespace {
 
 constexpr int FBM = 128, FBN = 128, FBK = 64, FUK = 16;
-constexpr int FSTAGES = 4;
+constexpr int FSTAGES = 3;
 constexpr int F_A_BYTES = FBM * FBK * 2;  // 16 KiB
 constexpr int F_B_BYTES = FBN * FBK * 2;  // 16 KiB
 constexpr int F_RING_BYTES = FSTAGES * (F_A_BYTES + F_B_BYTES);
-constexpr int F_MAIN_RAW = leaf::DL_SMEM_BYTES > F_RING_BYTES ? leaf::DL_SMEM_BYTES : F_RING_BYTES;  // leaf arrays and ring alias
+constexpr int F_STC_BYTES = FBM * FBN * 4, F_STH_BYTES = FBM * FBN * 2;  // result tile staged for the TMA stores
+constexpr int F_GEMM_BYTES = F_RING_BYTES + F_STC_BYTES + F_STH_BYTES;
+constexpr int F_MAIN_RAW = leaf::DL_SMEM_BYTES > F_GEMM_BYTES ? leaf::DL_SMEM_BYTES : F_GEMM_BYTES;  // leaf arrays alias ring + staging
 constexpr int F_MAIN_BYTES = ((F_MAIN_RAW + 1023) / 1024) * 1024;
 constexpr int F_PROG_CAP = 16 * 1024;     // the step program is staged in shared memory when it fits
 constexpr int F_BAR_BYTES = 256;
@@ -41,7 +43,7 @@ constexpr int F_SMEM_BYTES = F_MAIN_BYTES + F_BAR_BYTES + F_PROG_CAP + 1024;  //
 constexpr int F_THREADS = leaf::DL_THREADS;  // 16 warps: 0-7 epilogue, 8 TMA producer, 9 MMA issuer; all 16 in a leaf
 constexpr int F_EPI_WARPS = 8;
 constexpr int F_TMEM_COLS = 256;             // two 128-column fp32 accumulators
-static_assert(F_MAIN_BYTES % 1024 == 0 && F_MAIN_BYTES >= leaf::DL_SMEM_BYTES && F_MAIN_BYTES >= F_RING_BYTES, "smem layout");
+static_assert(F_MAIN_BYTES % 1024 == 0 && F_MAIN_BYTES >= leaf::DL_SMEM_BYTES && F_MAIN_BYTES >= F_GEMM_BYTES, "smem layout");
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
@@ -52,13 +54,17 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // All CTAs of the grid: every global store (and every shared-memory store of a leaf) made before the barrier is visible
 // to every generic-proxy AND async-proxy (TMA) access made after it.
-__device__ __forceinline__ void grid_step_barrier(unsigned* bar, unsigned target) {
+__device__ __forceinline__ void grid_step_barrier(unsigned* bar, unsigned target, long long* dbg_slot) {
     fence_proxy_async_all();
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        if (dbg_slot) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); *dbg_slot = t_; }
+        // release at gpu scope (cumulative over the CTA's writes ordered before it by the bar.sync above)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
         while (ld_acquire_gpu(bar) < target) { }
+        // The fence is what invalidates this SM's L1: the other threads' plain loads after the barrier (addends, leaf
+        // input) must not hit lines cached before another CTA -- or this CTA's own TMA store, which bypasses L1 --
+        // rewrote them.  (Without it a general matrix lost whole Schur updates: first backward error 4e-2 vs 2e-4.)
         __threadfence();
     }
     __syncthreads();
@@ -101,12 +107,18 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
     uint64_t* empty = full + FSTAGES;
     uint64_t* tfull = empty + FSTAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* lbar = tempty + 2;  // the leaf's tensor-core products (leaf.cuh, kTc)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 1);
     uint8_t* sprog = smem + F_MAIN_BYTES + F_BAR_BYTES;
 
     const int tid = threadIdx.x;
     const uint32_t warp = tid >> 5, lane = tid & 31;
     const int cta = blockIdx.x, G = gridDim.x;
+    // GEMM tiles are dealt starting at CTA 2: CTAs 0 and 1 run the leaves (their instruction cache holds leaf code and
+    // they are the last to reach the barrier after a leaf), the others wait at the barrier with the GEMM code hot
+    const int first_cta = G > 2 ? 2 : 0;
+    const int slot0 = (cta - first_cta + G) % G;
+    const bool prof = a.dbg_clk != nullptr && cta == first_cta;  // the CTA that takes tile 0 of every GEMM step
 
     // ---- the step program: staged in shared memory when it fits (it is read at the head of every step, on the chain)
     const int prog_bytes = a.num_steps * (int)sizeof(FusedStep) + a.num_problems * (int)sizeof(FusedProblem);
@@ -124,7 +136,9 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
         for (int i = 0; i < FM_COUNT; ++i) {
             ptx::prefetch_tmap(&maps.a[i]);
             ptx::prefetch_tmap(&maps.b[i]);
+            ptx::prefetch_tmap(&maps.h[i]);
         }
+        ptx::prefetch_tmap(&maps.c);
         for (int i = 0; i < FSTAGES; ++i) {
             ptx::mbar_init(&full[i], 1);   // the producer's arrive.expect_tx
             ptx::mbar_init(&empty[i], 1);  // one tcgen05.commit
@@ -133,6 +147,7 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
             ptx::mbar_init(&tfull[i], 1);             // one tcgen05.commit
             ptx::mbar_init(&tempty[i], F_EPI_WARPS);  // one arrival per epilogue warp
         }
+        ptx::mbar_init(lbar, 1);
         ptx::fence_mbar_init();
     }
     if (warp == F_EPI_WARPS + 1) ptx::tmem_alloc<1>(tmem_slot, F_TMEM_COLS);
@@ -145,11 +160,12 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
     uint32_t acc_iter = 0;          // accumulator tiles this CTA has gone through (MMA issuer and epilogue warps)
     float mx = 0.f;                 // largest scaled fp16 magnitude written (overflow detection)
     const uint32_t idesc = make_idesc_f16(FBM, FBN, a.bf16 != 0, true, false);
+    leaf::LeafTc ltc{tmem_base, lbar, 0u};
 
     // development aid (mplu_debug_fused_profile): CTA 0 stamps clock64 at the head of every step and at the end,
     // followed by %globaltimer (ns) at both ends of the launch for calibration
     auto stamp = [&](int slot, bool wall) {
-        if (a.dbg_clk && cta == 0 && tid == 0) {
+        if (prof && tid == 0) {
             long long t_;
             if (wall) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) :: "memory");
             else asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory");
@@ -164,10 +180,10 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
         if (st.kind == FS_LEAF) {
             if (cta < 2) {
                 const long long off16 = (long long)(st.k0 - st.T) + (long long)st.k0 * a.ld16;
-                leaf::diag_lu_body(reinterpret_cast<float*>(smem), cta, a.W, a.ldw, st.k0,
+                leaf::diag_lu_body_tc(reinterpret_cast<float*>(smem), cta, a.W, a.ldw, st.k0,
                                    reinterpret_cast<uint16_t*>(a.Linv16) + off16, reinterpret_cast<uint16_t*>(a.Uinv16) + off16,
                                    a.ld16, a.Linv32, a.Uinv32, a.inv_scales + 4 * (st.T / leaf::DB), st.first_in_tile, st.blk,
-                                   a.bf16, a.status, nullptr, st.valid);
+                                   a.bf16, a.status, (a.dbg_clk && cta == 0 && st.blk % 16 == 8) ? a.dbg_clk + 300 : nullptr, st.valid, ltc);
             }
         } else {
             const int ntiles = st.tile_end[st.num_problems - 1];
@@ -175,7 +191,7 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                 // ------------------------------------------------------------ TMA producer
                 if (lane == 0) {
                     fence_proxy_async_all();  // the previous step's generic-proxy stores (made visible by the barrier) -> TMA
-                    for (int t = cta; t < ntiles; t += G) {
+                    for (int t = slot0; t < ntiles; t += G) {
                         const TileRef r = tile_ref(st, probs, t);
                         const FusedProblem& p = *r.p;
                         const CUtensorMap* tmA = &maps.a[p.a_map];
@@ -198,7 +214,7 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                 __syncwarp();
             } else if (warp == F_EPI_WARPS + 1) {
                 // ------------------------------------------------------------ MMA issuer
-                for (int t = cta; t < ntiles; t += G, ++acc_iter) {
+                for (int t = slot0; t < ntiles; t += G, ++acc_iter) {
                     const TileRef r = tile_ref(st, probs, t);
                     const uint32_t as = acc_iter & 1, aphase = (acc_iter >> 1) & 1;
                     ptx::mbar_wait(&tempty[as], aphase ^ 1);
@@ -229,23 +245,28 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                 // ------------------------------------------------------------ epilogue: warp w reads TMEM lanes 32*(w%4)..,
                 // columns [64*(w/4), +64) of the tile as two chunks of 32 (one row per thread)
                 const uint32_t q = warp & 3, half = warp >> 2;
-                for (int t = cta; t < ntiles; t += G, ++acc_iter) {
+                // the result tile is staged in shared memory as [column][row] (rows contiguous, like the matrix) and leaves
+                // as two TMA tile stores: a thread's 64 fp32 + 64 16-bit scalar global stores per tile kept the epilogue
+                // at ~6k cycles, LSU-issue bound, on the critical path of every step
+                float* stC = reinterpret_cast<float*>(smem + F_RING_BYTES);
+                uint16_t* stH = reinterpret_cast<uint16_t*>(smem + F_RING_BYTES + F_STC_BYTES);
+                bool stored = false;
+                for (int t = slot0; t < ntiles; t += G, ++acc_iter) {
                     const TileRef r = tile_ref(st, probs, t);
                     const FusedProblem& p = *r.p;
-                    const int row = r.mt * FBM + q * 32 + lane;
-                    const int colbase = r.nt * FBN + half * 64;
+                    const int trow = q * 32 + lane;          // row inside the tile
+                    const int tcol0 = half * 64;             // first of this warp's 64 columns inside the tile
                     float alpha = p.alpha;
                     if (p.alpha_p1) alpha *= *p.alpha_p1;
                     if (p.alpha_p2) alpha *= *p.alpha_p2;
                     const float hs = p.hscale_p ? *p.hscale_p : 1.f;
                     float cin[2][32];
                     if (p.accumulate) {  // addend loads in flight while the MMAs of this tile run
+                        const float* src = a.W + (p.c_r0 + r.mt * FBM + trow) + (long long)(p.c_c0 + r.nt * FBN + tcol0) * a.ldw;
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float* src = p.C + row + (long long)(colbase + c * 32) * p.ldc;
+                        for (int c = 0; c < 2; ++c)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) cin[c][j] = src[(long long)j * p.ldc];
-                        }
+                            for (int j = 0; j < 32; ++j) cin[c][j] = src[(long long)(c * 32 + j) * a.ldw];
                     } else {
 #pragma unroll
                         for (int c = 0; c < 2; ++c)
@@ -255,45 +276,45 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                     const uint32_t as = acc_iter & 1, aphase = (acc_iter >> 1) & 1;
                     ptx::mbar_wait(&tfull[as], aphase);
                     ptx::tc_fence_after();
+                    if (prof && tid == 0 && t == 0 && s < 61) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[64 + 3 * s] = t_; }
+                    if (stored) {  // the staging area is free once the previous tile's stores have read it
+                        if (tid == 0) ptx::bulk_wait_group_read0();
+                        ptx::named_bar_sync(1, F_EPI_WARPS * 32);
+                    }
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + as * FBN + half * 64 + c * 32, v);
                         ptx::tmem_ld_wait();
-                        if (c == 1) {  // accumulator fully read: hand the TMEM stage back before the last stores
+                        if (c == 1) {  // accumulator fully read: hand the TMEM stage back
                             ptx::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) ptx::mbar_arrive(&tempty[as]);
                         }
-                        const int col0 = colbase + c * 32;
-                        float out[32];
+                        const int sidx = (tcol0 + c * 32) * FBM + trow;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) out[j] = fmaf(alpha, __uint_as_float(v[j]), cin[c][j]);
-                        if (p.C) {
-                            float* dst = p.C + row + (long long)col0 * p.ldc;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) dst[(long long)j * p.ldc] = out[j];
-                        }
-                        if (p.H && (row < p.h_rows || col0 < p.h_cols)) {  // h_cols is a multiple of 32 here
-                            if (a.bf16) {
-                                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.H) + row + (long long)col0 * p.ldh;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) dst[(long long)j * p.ldh] = __float2bfloat16_rn(out[j] * hs);
-                            } else {
-                                __half* dst = reinterpret_cast<__half*>(p.H) + row + (long long)col0 * p.ldh;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float hv = out[j] * hs;
-                                    dst[(long long)j * p.ldh] = __float2half_rn(hv);
-                                    mx = fmaxf(mx, fabsf(hv));
-                                }
-                            }
+                        for (int j = 0; j < 32; ++j) {
+                            const float o = fmaf(alpha, __uint_as_float(v[j]), cin[c][j]);
+                            stC[sidx + j * FBM] = o;
+                            const float hv = o * hs;
+                            if (a.bf16) stH[sidx + j * FBM] = __bfloat16_as_ushort(__float2bfloat16_rn(hv));
+                            else { stH[sidx + j * FBM] = __half_as_ushort(__float2half_rn(hv)); mx = fmaxf(mx, fabsf(hv)); }
                         }
                     }
+                    ptx::fence_proxy_async();  // the staged tile -> async proxy
+                    ptx::named_bar_sync(1, F_EPI_WARPS * 32);
+                    if (tid == 0) {
+                        if (p.c_r0 >= 0) ptx::tma_store_2d(&maps.c, stC, p.c_r0 + r.mt * FBM, p.c_c0 + r.nt * FBN);
+                        if (p.h_map >= 0) ptx::tma_store_2d(&maps.h[p.h_map], stH, p.h_r0 + r.mt * FBM, p.h_c0 + r.nt * FBN);
+                        ptx::bulk_commit_group();
+                    }
+                    stored = true;
+                    if (prof && tid == 0 && s < 61) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[64 + 3 * s + 1] = t_; }
                 }
+                if (stored && tid == 0) ptx::bulk_wait_group0();  // this step's tile stores are performed before the barrier
             }
         }
-        grid_step_barrier(a.barrier, (unsigned)G * (unsigned)(s + 1));
+        grid_step_barrier(a.barrier, (unsigned)G * (unsigned)(s + 1), (prof && s < 61) ? a.dbg_clk + 64 + 3 * s + 2 : nullptr);
     }
     stamp(a.num_steps, false);
     stamp(a.num_steps + 2, true);

@@ -11,25 +11,24 @@ namespace mplu {
 // the 16-bit arrays a product can take its operands from (one TMA map each as A operand and as B operand)
 enum FusedMap : int { FM_WH = 0, FM_FH = 1, FM_LINV = 2, FM_UINV = 3, FM_T1 = 4, FM_T2 = 5, FM_COUNT = 6 };
 
-// out(m,n) = (accumulate ? C : 0) + alpha * sum_k A(m,k) B(k,n); same meaning as GemmParams (gemm_tc.h).
-// M, N multiples of 128, K a multiple of 64.
+// out(m,n) = (accumulate ? W(c_r0+m, c_c0+n) : 0) + alpha * sum_k A(m,k) B(k,n); same meaning as GemmParams (gemm_tc.h).
+// M, N multiples of 128, K a multiple of 64.  The fp32 result goes to the working matrix W at (c_r0, c_c0), the 16-bit
+// copy (scaled by *hscale_p) to array h_map at (h_r0, h_c0); both are written as whole 128x128 tiles (TMA stores).
 struct alignas(16) FusedProblem {
     int M, N, K;
     int a_map, a_r0, a_c0;  // A block origin inside its parent array: (row m0, col k0)
     int b_map, b_r0, b_c0;  // B block origin: (row k0, col n0)
     int tri;                // GemmTri
     int accumulate;
-    int h_rows, h_cols;     // the 16-bit copy is written where (m < h_rows || n < h_cols)
     float alpha;            // times *alpha_p1 times *alpha_p2 (null = 1)
-    int ldc, ldh;
-    float* C;               // fp32 result (null: none)
-    void* H;                // 16-bit result scaled by *hscale_p (null: none)
+    int c_r0, c_c0;         // c_r0 < 0: no fp32 result
+    int h_map, h_r0, h_c0;  // h_map < 0: no 16-bit result
+    int pad_;
     const float* alpha_p1;
     const float* alpha_p2;
     const float* hscale_p;
-    long long pad_;
 };
-static_assert(sizeof(FusedProblem) == 112, "FusedProblem layout");
+static_assert(sizeof(FusedProblem) == 96, "FusedProblem layout");
 
 enum FusedStepKind : int { FS_GEMM = 0, FS_LEAF = 1 };
 struct alignas(16) FusedStep {
@@ -41,8 +40,10 @@ struct alignas(16) FusedStep {
 static_assert(sizeof(FusedStep) == 48, "FusedStep layout");
 
 struct alignas(64) FusedMaps {
-    CUtensorMap a[FM_COUNT];  // boxes of 64 (rows, contiguous) x 64
-    CUtensorMap b[FM_COUNT];  // boxes of 64 x 128
+    CUtensorMap a[FM_COUNT];  // operand loads, SWIZZLE_128B: boxes of 64 (rows, contiguous) x 64
+    CUtensorMap b[FM_COUNT];  //                              boxes of 64 x 128
+    CUtensorMap h[FM_COUNT];  // 16-bit result stores, unswizzled boxes of 128 x 128
+    CUtensorMap c;            // fp32 result stores into W, unswizzled boxes of 128 x 128
 };
 
 struct FusedArgs {

@@ -15,10 +15,12 @@ namespace {
 
 constexpr int RES_THREADS = 128;  // each thread owns 2 consecutive rows
 
-// partial[chunk][row] = sum_{c in chunk} A(row,c) * x(c)
+// partial[chunk][row] = sum_{c in chunk} A(row,c) * x(c);  kAbs: also abs_partial[chunk][row] = sum |A(row,c)| -- the row
+// sums behind ||A||_inf ride in the first residual, which streams all of A anyway, instead of a pass of their own
+template <bool kAbs>
 __global__ void __launch_bounds__(RES_THREADS)
 residual_partial_kernel(const double* __restrict__ A, long long lda, int n, const double* __restrict__ x,
-                        double* __restrict__ partial, int cols_per) {
+                        double* __restrict__ partial, int cols_per, double* __restrict__ abs_partial) {
     extern __shared__ double xs[];
     const int c0 = blockIdx.y * cols_per;
     const int c1 = min(n, c0 + cols_per);
@@ -28,7 +30,7 @@ residual_partial_kernel(const double* __restrict__ A, long long lda, int n, cons
     if (r0 >= n) return;
     const int nc = c1 - c0;
     const double* Ap = A + r0 + (long long)c0 * lda;
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, s0 = 0.0, s1 = 0.0;
     const bool vec = (r0 + 1 < n) && ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     if (vec) {
         int c = 0;
@@ -41,21 +43,33 @@ residual_partial_kernel(const double* __restrict__ A, long long lda, int n, cons
                 const double xv = xs[c + u];
                 a0 = fma(v[u].x, xv, a0);
                 a1 = fma(v[u].y, xv, a1);
+                if (kAbs) { s0 += fabs(v[u].x); s1 += fabs(v[u].y); }
             }
         }
         for (; c < nc; ++c) {
             const double2 v = __ldg(reinterpret_cast<const double2*>(Ap + (long long)c * lda));
             a0 = fma(v.x, xs[c], a0);
             a1 = fma(v.y, xs[c], a1);
+            if (kAbs) { s0 += fabs(v.x); s1 += fabs(v.y); }
         }
     } else {
         for (int c = 0; c < nc; ++c) {
-            a0 = fma(__ldg(Ap + (long long)c * lda), xs[c], a0);
-            if (r0 + 1 < n) a1 = fma(__ldg(Ap + 1 + (long long)c * lda), xs[c], a1);
+            const double v0 = __ldg(Ap + (long long)c * lda);
+            a0 = fma(v0, xs[c], a0);
+            if (kAbs) s0 += fabs(v0);
+            if (r0 + 1 < n) {
+                const double v1 = __ldg(Ap + 1 + (long long)c * lda);
+                a1 = fma(v1, xs[c], a1);
+                if (kAbs) s1 += fabs(v1);
+            }
         }
     }
     partial[(long long)blockIdx.y * n + r0] = a0;
     if (r0 + 1 < n) partial[(long long)blockIdx.y * n + r0 + 1] = a1;
+    if (kAbs) {
+        abs_partial[(long long)blockIdx.y * n + r0] = s0;
+        if (r0 + 1 < n) abs_partial[(long long)blockIdx.y * n + r0 + 1] = s1;
+    }
 }
 
 __device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v) {
@@ -65,12 +79,15 @@ __device__ __forceinline__ void atomic_max_double_nonneg(double* addr, double v)
 // r = b - sum_chunks partial; norms[0] = max|r|, norms[1] = max|x|   (norms zeroed by the launcher)
 __global__ void residual_finish_kernel(const double* __restrict__ partial, int n, int nchunk,
                                        const double* __restrict__ b, const double* __restrict__ x,
-                                       double* __restrict__ r, double* norms) {
+                                       double* __restrict__ r, double* norms, const double* __restrict__ abs_partial,
+                                       double* anorm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double rv = 0.0, xv = 0.0;
+    double rv = 0.0, xv = 0.0, av = 0.0;
     if (i < n) {
         double s = 0.0;
         for (int c = 0; c < nchunk; ++c) s += partial[(long long)c * n + i];
+        if (abs_partial)
+            for (int c = 0; c < nchunk; ++c) av += abs_partial[(long long)c * n + i];
         rv = b[i] - s;
         r[i] = rv;
         rv = fabs(rv);
@@ -79,10 +96,12 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
     for (int o = 16; o > 0; o >>= 1) {
         rv = fmax(rv, __shfl_xor_sync(0xffffffffu, rv, o));
         xv = fmax(xv, __shfl_xor_sync(0xffffffffu, xv, o));
+        av = fmax(av, __shfl_xor_sync(0xffffffffu, av, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomic_max_double_nonneg(&norms[0], rv);
         atomic_max_double_nonneg(&norms[1], xv);
+        if (anorm) atomic_max_double_nonneg(anorm, av);
     }
 }
 
@@ -321,12 +340,19 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
 }  // namespace
 
 int launch_residual(const double* A, long long lda, int n, const double* x, const double* b, double* r,
-                    double* partial, int nchunk, double* norms, cudaStream_t st) {
+                    double* partial, int nchunk, double* norms, cudaStream_t st, double* abs_partial, double* anorm) {
     const int cols_per = (n + nchunk - 1) / nchunk;
     dim3 grid((n + 2 * RES_THREADS - 1) / (2 * RES_THREADS), nchunk);
-    residual_partial_kernel<<<grid, RES_THREADS, cols_per * sizeof(double), st>>>(A, lda, n, x, partial, cols_per);
+    const bool with_abs = abs_partial != nullptr && anorm != nullptr;
+    if (with_abs) {
+        residual_partial_kernel<true><<<grid, RES_THREADS, cols_per * sizeof(double), st>>>(A, lda, n, x, partial, cols_per, abs_partial);
+        cudaMemsetAsync(anorm, 0, sizeof(double), st);
+    } else {
+        residual_partial_kernel<false><<<grid, RES_THREADS, cols_per * sizeof(double), st>>>(A, lda, n, x, partial, cols_per, nullptr);
+    }
     cudaMemsetAsync(norms, 0, 2 * sizeof(double), st);
-    residual_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, n, nchunk, b, x, r, norms);
+    residual_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, n, nchunk, b, x, r, norms, with_abs ? abs_partial : nullptr,
+                                                            with_abs ? anorm : nullptr);
     return (int)cudaGetLastError();
 }
 

@@ -26,6 +26,9 @@ int launch_first_touch(const double* A, long long lda, int n, float* W, long lon
 // [slot0, slot0 + nslots) of rowsum_part), and the final ||A||_inf over the first nslots slots
 int launch_first_touch_cols(const double* A, long long lda, int n, float* W, long long ldw, int npad, int cb, int ce,
                             float* amax, double* rowsum_part, int slot0, int nslots, cudaStream_t st);
+// the same for rows [0, rows) of the columns [cb, ce) only, without row sums (lazy first touch: first block row)
+int launch_first_touch_block(const double* A, long long lda, int n, float* W, long long ldw, int npad, int rows, int cb, int ce,
+                             float* amax, cudaStream_t st);
 int launch_anorm(const double* rowsum_part, int n, int nslots, double* anorm, cudaStream_t st);
 int launch_scales(const float* amax, float* scales, int target_exp_a, int exp_l, int bf16, cudaStream_t st);
 int launch_shadow_cast(const float* W, long long ldw, void* H, long long ldh, int rows, int cols, const float* scale,
@@ -42,8 +45,10 @@ int launch_diag_lu(float* W, long long ldw, int k0, void* Linv16, void* Uinv16, 
 
 // ir.cu
 // r = b - A*x (fp64), ||r||_inf and ||x||_inf into norms[0], norms[1]
+// abs_partial (nchunk * n doubles) / anorm non-null: the same pass also forms the row sums of |A| and ||A||_inf
 int launch_residual(const double* A, long long lda, int n, const double* x, const double* b, double* r,
-                    double* partial, int nchunk, double* norms, cudaStream_t st);
+                    double* partial, int nchunk, double* norms, cudaStream_t st, double* abs_partial = nullptr,
+                    double* anorm = nullptr);
 // solve L U d = r with the fp32 factors in W (unit-lower L, U), blocked by kDiagBlock with the fp32 inverses of the
 // diagonal blocks; y (fp32 work vectors, 2*npad floats); ready = one device word (step counter of the sweep).  d_out (fp64) = solution; if x_accum != null, x_accum += d.
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,

@@ -111,7 +111,14 @@ int ensure_work(mplu_context* c, int n) {
     CKI(make_operand(&c->opT1, c->Tb1, nbc, nbc, nbc));
     CKI(make_operand(&c->opT2, c->Tb2, nbc, nbc, nbc));
     const Operand16* ops[FM_COUNT] = {&c->opWh, &c->opFh, &c->opLinv, &c->opUinv, &c->opT1, &c->opT2};
-    for (int i = 0; i < FM_COUNT; ++i) { c->fmaps.a[i] = ops[i]->mapA; c->fmaps.b[i] = ops[i]->mapB2; }
+    for (int i = 0; i < FM_COUNT; ++i) {
+        c->fmaps.a[i] = ops[i]->mapA;
+        c->fmaps.b[i] = ops[i]->mapB2;
+        const bool band = i == FM_LINV || i == FM_UINV, scratch = i == FM_T1 || i == FM_T2;
+        if (make_tmap_plain(&c->fmaps.h[i], ops[i]->base, 2, band || scratch ? nbc : np, scratch ? nbc : np, (uint64_t)ops[i]->ld,
+                            kDiagBlock, kDiagBlock)) return MPLU_E_TMAP;
+    }
+    if (make_tmap_plain(&c->fmaps.c, c->W, 4, np, np, np, kDiagBlock, kDiagBlock)) return MPLU_E_TMAP;
     return 0;
 }
 
@@ -236,6 +243,13 @@ GemmParams gemm_params(const mplu_context* c, const GemmCall& g, const Lane& ln)
     p.a_r0 = g.a_r0; p.a_c0 = g.a_c0; p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
     p.C = g.C; p.ldc = g.ldc;
     p.Cin = g.accumulate ? g.C : nullptr; p.ldcin = g.ldc;
+    if (g.accumulate && g.from_a) {  // the tile's first update: addend = fp32(A) of the same block, cast in the epilogue
+        const long long off = g.C - c->W;
+        p.Cin = nullptr;
+        p.cin64 = c->aref;
+        p.cin64_r0 = (int)(off % g.ldc);
+        p.cin64_c0 = (int)(off / g.ldc);
+    }
     p.H = g.H; p.ldh = g.ldh;
     p.h_rows = g.h_rows; p.h_cols = g.h_cols;
     p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2;
@@ -288,9 +302,23 @@ void rec_gemm_step(mplu_context* c, const GemmCall* calls, int count) {
         p.b_map = fused_map_of(c, g.B); p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
         p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
         p.accumulate = g.accumulate ? 1 : 0;
-        p.h_rows = g.h_rows; p.h_cols = g.h_cols;
         p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2; p.hscale_p = g.hscale_p;
-        p.C = g.C; p.ldc = (int)g.ldc; p.H = g.H; p.ldh = (int)g.ldh;
+        p.c_r0 = p.c_c0 = -1;
+        if (g.C) {  // the fp32 result always lives in W
+            const long long off = g.C - c->W;
+            p.c_r0 = (int)(off % g.ldc); p.c_c0 = (int)(off / g.ldc);
+            if (g.ldc != c->npad) c->rec->unsupported = true;
+        }
+        p.h_map = -1;
+        if (g.H) {  // the 16-bit copy is a whole-tile store: inside a GETRF every product shadows all of its result
+            int arr = 0, hr = 0, hc = 0;
+            if (trace_locate16(c, g.H, g.ldh, &arr, &hr, &hc) && (g.h_rows >= g.M || g.h_cols >= g.N)) {
+                p.h_map = arr - TA_WH; p.h_r0 = hr; p.h_c0 = hc;
+            } else {
+                c->rec->unsupported = true;
+            }
+        }
+        if (g.accumulate && !g.C) c->rec->unsupported = true;
         c->rec->problems.push_back(p);
         tiles += (g.M / kDiagBlock) * (g.N / kDiagBlock);
         st.tile_end[st.num_problems++] = tiles;
@@ -400,16 +428,17 @@ struct Sched {
 
     // A[r0:r1, c0:c1) -= L[r0:r1, k0:k1) * U[k0:k1, c0:c1): operands from the factor shadow Fh, result in W and,
     // where asked, in the trailing shadow Wh (the reference's cublasDgemm, MPF.cu:230-239)
-    GemmCall schur_call(int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
+    GemmCall schur_call(int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols, bool first = false) const {
         GemmCall g{&c->opFh, r0, k0, &c->opFh, k0, c0, r1 - r0, c1 - c0, k1 - k0, Wp(r0, c0), ld, true,
                    Whp(r0, c0), ld, h_rows, h_cols, 1.f, sc(SC_NEG_LA_INV), nullptr, sc(SC_A)};
+        g.from_a = first && c->lazy;  // update 0 of a block that the lazy first touch left in the caller's fp64 matrix
         // updates much larger than a diagonal tile: their C / shadow traffic is touched once per launch and exceeds L2,
         // so it goes through the streaming cache policy (the tile-sized updates of the chain lane stay cacheable)
         g.stream_c = (long long)(r1 - r0) * (c1 - c0) >= (8ll << 20);
         return g;
     }
-    int schur(const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols) const {
-        return run_gemm(c, ln, schur_call(r0, r1, c0, c1, k0, k1, h_rows, h_cols));
+    int schur(const Lane& ln, int r0, int r1, int c0, int c1, int k0, int k1, int h_rows, int h_cols, bool first = false) const {
+        return run_gemm(c, ln, schur_call(r0, r1, c0, c1, k0, k1, h_rows, h_cols, first));
     }
     // U[k0:k0+w, c0:c1) = inv(L[k0:k0+w)) * A[k0:k0+w, c0:c1)   (inverse of the block inside tile T, one GEMM)
     GemmCall trsm_u_call(int T, int k0, int w, int c0, int c1) const {
@@ -453,6 +482,7 @@ struct Sched {
             const int rc = getrf(ln, T, c0, w);
             c->rec = nullptr;
             if (rc) return rc;
+            if (r.unsupported) return MPLU_E_ARG;
             const size_t sb = r.steps.size() * sizeof(FusedStep), pb = r.problems.size() * sizeof(FusedProblem);
             const size_t off = c->fprog_host.size();
             if (off + sb + pb > c->fprog_cap) return MPLU_E_ARG;
@@ -862,7 +892,7 @@ int enqueue_factorization_left(mplu_context* c) {
     // U(k+1,.) reads -- the rest would be overwritten by update k+1 anyway, and the full-shadow epilogue costs the
     // tall update a fifth of its rate (855 vs 1109 TFLOP/s at 30720 x 30720 x 2048)
     auto big_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1, bool last) -> int {
-        return S.schur(ln, r0, npad, c0, c1, k0, k1, last ? npad - r0 : NB, last ? c1 - c0 : 0);
+        return S.schur(ln, r0, npad, c0, c1, k0, k1, last ? npad - r0 : NB, last ? c1 - c0 : 0, k0 == 0);
     };
     auto timed_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1) -> int {
         // every rank-nb update of the bulk lane is timed with its own event pair for the roofline figure
@@ -906,7 +936,7 @@ int enqueue_factorization_left(mplu_context* c) {
             if (two) { CKI(step_event(c, j, EV_U, &ev)); CKI(ev_record(c, ev, chain.st)); }
         }
         u_done = false;
-        CKI(S.schur(chain, c0, two ? c1 : npad, c0, c1, kp, c0, (two ? c1 : npad) - c0, w));
+        CKI(S.schur(chain, c0, two ? c1 : npad, c0, c1, kp, c0, (two ? c1 : npad) - c0, w, kp == 0));
         CKI(mark(c, 2000 + j, chain.st));
         CKI(S.getrf(chain, c0, c0, w));
         CKI(mark(c, 3000 + j, chain.st));
@@ -1018,12 +1048,29 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     cudaStream_t st = c->stream;
     CK(cudaMemsetAsync(c->status, 0, sizeof(int), st));
     // left-looking schedule with at least two block columns: the first touch overlaps the first diagonal tile
-    const bool early = c->opts.schedule == MPLU_SCHED_LEFT && c->opts.early_scale != 0 && c->allow_early &&
-                       npad > effective_nb(c, npad) && c->opts.tile_ws == 0;
+    // Lazy first touch (left-looking schedule, order a multiple of 128, at least two block columns): only the first
+    // block column and block row are cast here; every other tile's first update reads its addend from the fp64 matrix
+    // itself (GemmParams::cin64), which removes the 12 n^2-byte cast pass.  The fp16 scale then comes from those two
+    // panels; a later entry that leaves the fp16 range under it raises the overflow bit and the caller redoes the
+    // factorization with the full first touch and the global scale (allow_early = false), like early_scale.
+    const int NB0 = effective_nb(c, npad);
+    const bool lazy = c->opts.schedule == MPLU_SCHED_LEFT && c->opts.lazy_touch != 0 && c->allow_early && npad == n &&
+                      npad > NB0 && c->opts.tile_ws == 0 && !c->trace;
+    const bool early = !lazy && c->opts.schedule == MPLU_SCHED_LEFT && c->opts.early_scale != 0 && c->allow_early &&
+                       npad > NB0 && c->opts.tile_ws == 0;
+    c->lazy = lazy;
+    c->anorm_pending = lazy;
     c->prologue_done = early;
-    c->used_early_scale = early && c->opts.precision != MPLU_BF16;
+    c->used_early_scale = (early || lazy) && c->opts.precision != MPLU_BF16;
     int pro_gemm = 0, pro_kern = 0;
-    if (early) {
+    if (lazy) {
+        if (!c->aref) CK(cudaMalloc(&c->aref, sizeof(ARef)));
+        const ARef href{dA, lda};
+        CK(cudaMemcpyAsync(c->aref, &href, sizeof(href), cudaMemcpyHostToDevice, st));  // pageable source: staged at once
+        CK(cudaMemsetAsync(c->amax, 0, sizeof(float), st));
+        CKI(launch_first_touch_cols(dA, lda, n, c->W, npad, npad, 0, NB0, c->amax, nullptr, 0, 64, st));
+        CKI(launch_first_touch_block(dA, lda, n, c->W, npad, npad, NB0, NB0, npad, c->amax, st));
+    } else if (early) {
         c->gemm_launches = c->kernel_launches = 0;
         CKI(prologue_left(c, dA, lda));
         pro_gemm = c->gemm_launches;
@@ -1045,12 +1092,12 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, (long long)early, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, (long long)early, (long long)lazy, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
         c->gemm_launches = 0;
-        c->kernel_launches = early ? 0 : 2;  // first touch + anorm
+        c->kernel_launches = early ? 0 : 2;  // first touch + anorm (lazy: the two panel casts)
         c->trail_count = 0;
         c->trail_flops = c->trail_bytes = 0;
         c->mark_count = 0;
@@ -1193,10 +1240,14 @@ int solve_impl(mplu_context* c, const double* dA, long long lda, const double* d
     double first_be = -1.0;
     const int max_iters = c->opts.max_iters > 0 ? c->opts.max_iters : 30;
     for (;;) {
-        CKI(launch_residual(dA, lda, n, dx, db, c->r, c->partial, c->nchunk, c->norms, st));
+        // lazy first touch: ||A||_inf rides in the first residual pass (it streams all of A anyway)
+        const bool with_anorm = c->anorm_pending;
+        CKI(launch_residual(dA, lda, n, dx, db, c->r, c->partial, c->nchunk, c->norms, st, with_anorm ? c->rowsum_part : nullptr,
+                            with_anorm ? c->anorm : nullptr));
+        c->anorm_pending = false;
         c->kernel_launches += 2;
         CK(cudaMemcpyAsync(h_norms, c->norms, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (first_be < 0) CK(cudaMemcpyAsync(h_an, c->anorm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (first_be < 0 || with_anorm) CK(cudaMemcpyAsync(h_an, c->anorm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const double be = h_norms[0] / (h_an[0] * h_norms[1] + h_an[1]);
         if (first_be < 0) first_be = be;
@@ -1286,6 +1337,7 @@ void mplu_default_options(mplu_options* o) {
     o->early_scale = 0;
     o->fuse_w = 2048;
     o->fuse_ctas = 16;
+    o->lazy_touch = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -1330,7 +1382,7 @@ void mplu_destroy(mplu_context* c) {
     free_work(c);
     cudaFree(c->scales); cudaFree(c->amax); cudaFree(c->anorm); cudaFree(c->norms); cudaFree(c->status); cudaFree(c->ready);
     cudaFree(c->dA_stage); cudaFree(c->db_stage); cudaFree(c->dx_stage);
-    cudaFree(c->gm_V); cudaFree(c->gm_w); cudaFree(c->gm_h); cudaFree(c->gm_zero);
+    cudaFree(c->gm_V); cudaFree(c->gm_w); cudaFree(c->gm_h); cudaFree(c->gm_zero); cudaFree(c->aref);
     if (c->tile) { mplu_destroy(c->tile); c->tile = nullptr; }
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->trail_ev) if (e) cudaEventDestroy(e);
@@ -1693,6 +1745,18 @@ int mplu_debug_timeline(mplu_context* c, int* tags, float* ms, int max) {
     return n;
 }
 
+// test hook: the fp32 inverses of the unit-lower / upper factor of diagonal 128-block `blk` (column-major 128 x 128 each,
+// device or host destination) as the triangular solves use them
+int mplu_debug_block_inverses(mplu_context* c, int blk, float* Linv, float* Uinv) {
+    if (!c || !c->factored || blk < 0 || blk >= c->npad / kDiagBlock || !Linv || !Uinv) return MPLU_E_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t bytes = (size_t)kDiagBlock * kDiagBlock * sizeof(float);
+    CK(cudaMemcpy(Linv, c->Linv32 + (size_t)blk * kDiagBlock * kDiagBlock, bytes, cudaMemcpyDefault));
+    CK(cudaMemcpy(Uinv, c->Uinv32 + (size_t)blk * kDiagBlock * kDiagBlock, bytes, cudaMemcpyDefault));
+    return 0;
+}
+
 // development aid: per-step time stamps of the fused GETRF launches.  enable: takes effect at the next schedule capture.
 // mplu_debug_fused_profile: for fused launch `launch` of the last factorization writes, per step, (kind, tiles, K of the
 // first product | leaf origin, clock64 at the step's head) as 4 long longs, then one record (-1, 0, ns of the whole
@@ -1701,6 +1765,7 @@ int mplu_debug_fused_profile_enable(mplu_context* c, int on) {
     if (!c) return MPLU_E_ARG;
     CK(cudaSetDevice(c->device));
     c->fprof_on = on != 0;
+    c->fprof_sub = on > 1;
     if (c->fprof_on && !c->fprof && c->fbar_cap > 0)
         CK(cudaMalloc(&c->fprof, (size_t)c->fbar_cap * mplu_context::kFusedProfSlots * sizeof(long long)));
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
@@ -1723,6 +1788,15 @@ int mplu_debug_fused_profile(mplu_context* c, int launch, long long* out, int ma
         out[4 * nrec + 1] = st.kind == FS_GEMM ? st.tile_end[st.num_problems - 1] : 1;
         out[4 * nrec + 2] = st.kind == FS_GEMM ? probs[st.first_problem].K : st.k0;
         out[4 * nrec + 3] = clk[s];
+        if (s < 61 && st.kind == FS_GEMM && c->fprof_sub) {  // sub-stamps relative to the step's head, packed into field 1
+            const long long t0 = clk[s];
+            auto rel = [&](int i) { long long d = clk[64 + 3 * s + i] - t0; return d < 0 ? 0 : (d > 0xFFFFF ? 0xFFFFF : d); };
+            out[4 * nrec + 1] |= (rel(0) << 20) | (rel(1) << 40);
+            out[4 * nrec + 2] |= rel(2) << 20;
+        }
+    }
+    for (int i = 0; i < 48 && nrec < max_records; ++i, ++nrec) {  // phase stamps of one leaf of the launch (CTA 0's clock)
+        out[4 * nrec] = -2; out[4 * nrec + 1] = i; out[4 * nrec + 2] = 0; out[4 * nrec + 3] = clk[300 + i];
     }
     if (nrec < max_records) {
         out[4 * nrec] = -1; out[4 * nrec + 1] = 0;

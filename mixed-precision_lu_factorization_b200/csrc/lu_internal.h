@@ -59,13 +59,18 @@ struct mplu_context {
     // left-looking prologue (first touch overlapped with the first diagonal tile)
     cudaEvent_t ev_pro[2] = {nullptr, nullptr};
     bool prologue_done = false, used_early_scale = false, allow_early = true;
+    // lazy first touch (left-looking schedule): only the first block column / block row of A are cast up front, every
+    // other tile takes the addend of its FIRST update from the original fp64 matrix (aref: device copy of {A, lda});
+    // ||A||_inf is then formed by the first residual pass (anorm_pending)
+    mplu::ARef* aref = nullptr;
+    bool lazy = false, anorm_pending = false;
     // dry run: non-null = record the schedule instead of launching it
     std::vector<TraceOp>* trace = nullptr;
     int trace_group = 0;
     // fused GETRF (getrf_fused.cu): step programs of the diagonal blocks, recorded once per (geometry, options) by running
     // the recursion with `rec` set, kept on the device; one barrier word per fused launch of a factorization
     struct FusedProg { int T, c0, w; size_t offset; int num_steps, num_problems; };
-    struct FusedRecorder { std::vector<mplu::FusedStep> steps; std::vector<mplu::FusedProblem> problems; };
+    struct FusedRecorder { std::vector<mplu::FusedStep> steps; std::vector<mplu::FusedProblem> problems; bool unsupported = false; };
     std::vector<FusedProg> fprogs;
     std::vector<unsigned char> fprog_host;
     std::vector<long long> fprog_key;
@@ -76,9 +81,9 @@ struct mplu_context {
     int fbar_cap = 0, fbar_next = 0;
     // development aid (mplu_debug_fused_profile): per fused launch of the last factorization, which program it ran and
     // a slice of kFusedProfSlots time stamps
-    static constexpr int kFusedProfSlots = 256;
+    static constexpr int kFusedProfSlots = 384;
     long long* fprof = nullptr;
-    bool fprof_on = false;
+    bool fprof_on = false, fprof_sub = false;
     std::vector<int> fprof_prog;  // launch index -> index into fprogs
     mplu::FusedMaps fmaps;
     // GEMM operand views (tensor maps) of the 16-bit arrays
@@ -141,6 +146,7 @@ struct GemmCall {
     const float* hscale_p;               // H = cvt16(out * *hscale_p)
     int tri = 0;                         // GemmTri: which operand is triangular (its zero part of K is skipped)
     bool stream_c = false;               // C / H are far larger than L2 and touched once: streaming cache policy
+    bool from_a = false;                 // accumulate onto the ORIGINAL fp64 matrix (a tile's first update) instead of C
 };
 
 // Where a piece of the schedule runs: stream + SM budget (0 = all SMs).

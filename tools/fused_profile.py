@@ -19,28 +19,45 @@ s = m.Solver(0)
 A, b = m.generate(n, seed=1)
 opts = m.default_options(nb=nb, **{k: int(v) for k, v in kv.items()})
 x, st = s.gesv(A, b, opts)
-lib.mplu_debug_fused_profile_enable(s._ctx, 1)
+lib.mplu_debug_fused_profile_enable(s._ctx, 2)
 for _ in range(2):
     x, st = s.gesv(A, b, opts)
 print(f"n={n} nb={nb} {kv} factor {st.factor_ms:.2f} ms solve {st.solve_ms:.2f} ms iters {st.iters} launches {st.kernel_launches}")
-buf = (C.c_longlong * (4 * 300))()
+buf = (C.c_longlong * (4 * 400))()
 for li in which:
-    k = lib.mplu_debug_fused_profile(s._ctx, li, buf, 300)
+    k = lib.mplu_debug_fused_profile(s._ctx, li, buf, 400)
     if k <= 0:
         print(f"launch {li}: not profiled")
         continue
     rec = [tuple(buf[4 * i: 4 * i + 4]) for i in range(k)]
+    leafclk = [r[3] for r in rec if r[0] == -2]
+    rec = [r for r in rec if r[0] != -2]
+    k = len(rec)
     end_clk, wall_ns = rec[-1][3], rec[-1][2]
     tot = end_clk - rec[0][3]
     print(f"launch {li}: {k - 1} steps, {tot} cycles, {wall_ns / 1e3:.1f} us wall = {tot / max(wall_ns, 1) * 1e3:.0f} MHz")
     summ = {}
     for i in range(k - 1):
         kind, tiles, kk, clk = rec[i]
+        sub = ((tiles >> 20) & 0xFFFFF, (tiles >> 40) & 0xFFFFF, (kk >> 20) & 0xFFFFF)  # tfull, epilogue done, barrier entered (CTA 0)
+        tiles &= 0xFFFFF; kk &= 0xFFFFF
         dur = (rec[i + 1][3] if i + 1 < k - 1 else end_clk) - clk
         key = "leaf" if kind == 1 else f"gemm K={kk} tiles={tiles}"
-        a = summ.setdefault(key, [0, 0])
-        a[0] += 1; a[1] += dur
+        a = summ.setdefault(key, [0, 0, 0, 0, 0])
+        a[0] += 1; a[1] += dur; a[2] += sub[0]; a[3] += sub[1]; a[4] += sub[2]
         if "verbose" in kv or k <= 40:
             print(f"   step {i:3d} {key:28s} {dur:8d} cyc")
-    for key, (cnt, cyc) in sorted(summ.items(), key=lambda t: -t[1][1]):
-        print(f"   {key:28s} x{cnt:3d}  {cyc:9d} cyc  avg {cyc // cnt:7d}  ({100.0 * cyc / tot:4.1f} %)")
+    if leafclk and leafclk[0]:
+        names = ["load", "P1+copy", "P2+I1", "P3"] + ["P1+copy", "P2+I1", "P3"] * 2 + ["P1+copy", "tail", "merge", "write-back"]
+        sub = leafclk[40:46]
+        sub3 = leafclk[46:49]
+        if len(sub3) == 3 and sub3[0]:
+            print(f"   P3 (kb=1), warp 3: woke up {sub3[0] - sub[3]} after the commit, TMEM->S {sub3[1] - sub3[0]}, barrier {sub3[2] - sub3[1]}")
+        leafclk = leafclk[:15]
+        if len(sub) == 6 and sub[0]:
+            print("   P3 (kb=1) on the tensor cores: " + " ".join(f"{nm}={sub[i + 1] - sub[i]}" for i, nm in enumerate(["stage", "fence+sync", "issue+commit", "wait", "TMEM->S+sync"])))
+        d = [leafclk[i + 1] - leafclk[i] for i in range(len(leafclk) - 1) if leafclk[i + 1] > 0]
+        print("   last leaf phases (cycles): " + " ".join(f"{nm}={v}" for nm, v in zip(names, d)))
+    for key, (cnt, cyc, s0, s1, s2) in sorted(summ.items(), key=lambda t: -t[1][1]):
+        print(f"   {key:28s} x{cnt:3d}  {cyc:9d} cyc  avg {cyc // cnt:7d}  ({100.0 * cyc / tot:4.1f} %)   CTA0 avg: accumulator ready @{s0 // cnt}, "
+              f"epilogue done @{s1 // cnt}, barrier entered @{s2 // cnt}")
