@@ -107,6 +107,28 @@ def cpu_lapack_baseline(n_sample):
                 sample=f"scipy/OpenBLAS dgetrf+dgetrs, n={n_sample}, {dt:.2f} s, max|x-1|={err:.1e}")
 
 
+def mpf_dropin_leg(m, n, reps=2):
+    """The repo's drop-in MPF(double *A, int N, int r, int *IPIV) (include/MPF.h; the reference's entry point,
+    /root/reference/MPF.h:3, with its semantics: fp16 pivot discovery + fp64 factors) timed the way benchmark.cpp:219-222
+    times the reference: the whole call from a host buffer, r = 32.  The reference arm (--impl reference) reports the
+    unmodified reference's MPF() at the same n as `reference_arm.mpf_same_n`."""
+    import numpy as np
+    import torch
+    A, _ = m.generate(n, seed=1, with_rhs=False)
+    hA0 = A.t().cpu().numpy()  # contiguous storage of A^T = column-major A
+    del A
+    torch.cuda.empty_cache()
+    times = []
+    for _ in range(reps + 1):
+        hA = np.asfortranarray(hA0.T.copy(order="F"))
+        t = time.perf_counter()
+        ipiv = m.MPF(hA, 32)
+        times.append(time.perf_counter() - t)
+    dt = min(times[1:])
+    return dict(value=flops(n) / dt / 1e12, unit="TFLOP/s", n=n, r=32, ms=1e3 * dt, what="repo drop-in MPF(), LU only, whole call incl. H2D/D2H",
+                identity_pivots=bool((ipiv == np.arange(1, n + 1)).all()))
+
+
 def run_reference(args):
     """--impl reference: the UNMODIFIED reference MPF() (oracle/_ref/libmpf_ref.so, built from /root/reference by
     oracle/Makefile; CUDA path, r = 32 as benchmark.cpp:220) timed as benchmark.cpp:219-222 times it (whole call,
@@ -158,13 +180,31 @@ def run_reference(args):
                 times.append(dt)
         ms = 1e3 * sum(times) / len(times)
         val = flops(n_ref) / (ms * 1e-3) / 1e12
+        same_n = None
+        if args.dropin_n > 0 and args.dropin_n != n_ref:  # the size the repo arm's mpf_dropin leg runs
+            nd = args.dropin_n
+            Ad0 = np.empty((nd, nd), dtype=np.float64, order="F")
+            orc.counter_matrix_into(Ad0, seed=1)
+            td = []
+            for it in range(3):
+                Ad = Ad0.copy(order="F")
+                ipd = np.arange(1, nd + 1, dtype=np.int32)
+                sys.stdout.flush()
+                saved = os.dup(1)
+                os.dup2(devnull, 1)
+                t = time.perf_counter()
+                f(Ad.ctypes.data, nd, 32, ipd.ctypes.data)
+                td.append(time.perf_counter() - t)
+                os.dup2(saved, 1)
+                os.close(saved)
+            same_n = dict(n=nd, ms=1e3 * min(td[1:]), value=flops(nd) / min(td[1:]) / 1e12, unit="TFLOP/s")
         line.update(value=val, ms_per_step=ms,
                     cpu_baseline=dict(value=val, unit="TFLOP/s", cores=1, kind="reference",
                                       sample=f"unmodified reference MPF() via oracle/_ref/libmpf_ref.so, n={n_ref}, r=32, one host "
                                              f"thread driving the GPU, whole call incl. cudaMalloc/H2D/D2H as benchmark.cpp:219-222"),
                     host_lapack=cpu,
                     e2e=dict(value=val, unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                    reference_arm=dict(kind="reference CUDA path (unmodified MPF.cu, -O3 sm_100a)", n=n_ref,
+                    reference_arm=dict(kind="reference CUDA path (unmodified MPF.cu, -O3 sm_100a)", n=n_ref, mpf_same_n=same_n,
                                        non_identity_pivots=int((ipiv != np.arange(1, n_ref + 1)).sum())))
         line["config"]["workload"] = f"n={n_ref} column-diagonally-dominant, reference MPF(A,n,32,ipiv) (LU only; it has no solve)"
     else:
@@ -299,6 +339,7 @@ def main():
     ap.add_argument("--impl", choices=["mplu", "reference"], default="mplu")
     ap.add_argument("--ref-n", type=int, default=0, help="size the reference arm runs (0 = the same n as the repo arm; the reference needs seconds per call)")
     ap.add_argument("--cpu-n", type=int, default=16384, help="sample size of the host LAPACK cpu_baseline leg (bounded: ~15 s of CPU work)")
+    ap.add_argument("--dropin-n", type=int, default=16384, help="size of the mpf_dropin leg: the repo's drop-in MPF() (reference semantics: fp16 pivot search + fp64 factors), whole call from host buffers; 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -430,6 +471,8 @@ def main():
                     headline_frac_of_peak=value / world / pk["tc_sustained"])
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = dict(cpu_lapack_baseline(min(n, args.cpu_n)), kind="port")
+        if args.dropin_n > 0:
+            line["mpf_dropin"] = mpf_dropin_leg(m, args.dropin_n)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

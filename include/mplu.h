@@ -72,7 +72,7 @@ typedef struct mplu_options {
                          (same factors bit for bit; n=32768: 35.8 vs 38.3 ms) */
     int eager;        /* MPLU_SCHED_LEFT: 1 (default) = the bulk lane spends each step's share of the remaining update work
                          ahead of need on the columns further right (balances the lanes); 0 = strictly left-looking */
-    int side_sms_left;/* MPLU_SCHED_LEFT: SMs of the chain lane (default 32; side_sms / side_sms_early are the right-looking
+    int side_sms_left;/* MPLU_SCHED_LEFT: SMs of the chain lane (default 24; side_sms / side_sms_early are the right-looking
                          schedule's) */
     int stream_c;     /* 1 (default): the tall rank-nb updates load / store their fp32 C and 16-bit shadow with the streaming
                          (evict-first) cache policy: that traffic is touched once per launch and far larger than L2 */
@@ -83,8 +83,9 @@ typedef struct mplu_options {
                          the overlap saves */
     int fuse_w;       /* GETRF of a diagonal block of at most fuse_w columns (multiple of 128) runs as ONE persistent launch
                          (leaves + every product between them, grid barriers instead of kernel boundaries); same factors
-                         bit for bit.  Default 2048 (a whole diagonal tile); 0 = one launch per leaf / product group */
-    int fuse_ctas;    /* CTAs (= SMs) of that launch, even, default 16 */
+                         bit for bit among fused widths.  Default 512 (measured best at n = 32768: the products above that width run faster as
+                         launches of the big GEMM kernel on the chain lane's SMs); 0 = one launch per leaf / product group */
+    int fuse_ctas;    /* CTAs (= SMs) of that launch, even, default 8 */
     int lazy_touch;   /* MPLU_SCHED_LEFT, n a multiple of 128: 1 (default) = no separate fp64 -> fp32 cast pass over A.  Only the
                          first block column / block row are cast up front (the fp16 scale comes from them); every other
                          tile's first Schur update takes its addend straight from the caller's fp64 matrix (the cast is fused

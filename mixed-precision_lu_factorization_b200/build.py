@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 # of the build stamp, so a plain build() afterwards rebuilds the default library
 NVCC_FLAGS += os.environ.get("MPLU_EXTRA_NVCC_FLAGS", "").split()
 
-SOURCES = ["gemm_tc.cu", "getrf_fused.cu", "panel.cu", "ir.cu", "lu.cu", "gmres.cu", "dist.cu", "generate.cu", "mpf_compat.cu"]
+SOURCES = ["gemm_tc.cu", "getrf_fused.cu", "panel.cu", "ir.cu", "lu.cu", "gmres.cu", "dist.cu", "generate.cu", "mpf_compat.cu", "dropin_kernels.cu"]
 
 
 def _nvcc() -> str:
@@ -77,6 +77,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    # the two drop-in kernels also as a static archive: a foreign translation unit that launches them itself (the way the
+    # reference's MPF.cu does) links this instead of taking the host stubs out of the shared library
+    ar = PKG / "libmplu_dropin.a"
+    if ar.exists():
+        ar.unlink()
+    subprocess.run(["ar", "rcs", str(ar), str(objdir / "dropin_kernels.o")], check=True)
     stamp_file.write_text(stamp)
     return LIB
 

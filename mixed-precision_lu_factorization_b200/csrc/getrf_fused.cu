@@ -54,13 +54,18 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // All CTAs of the grid: every global store (and every shared-memory store of a leaf) made before the barrier is visible
 // to every generic-proxy AND async-proxy (TMA) access made after it.
-__device__ __forceinline__ void grid_step_barrier(unsigned* bar, unsigned target, long long* dbg_slot) {
+// The barrier in two halves: what a CTA writes between its arrive and its wait is covered by its NEXT arrive.
+__device__ __forceinline__ void grid_step_arrive(unsigned* bar, long long* dbg_slot) {
     fence_proxy_async_all();
     __syncthreads();
     if (threadIdx.x == 0) {
         if (dbg_slot) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); *dbg_slot = t_; }
         // release at gpu scope (cumulative over the CTA's writes ordered before it by the bar.sync above)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    }
+}
+__device__ __forceinline__ void grid_step_wait(unsigned* bar, unsigned target) {
+    if (threadIdx.x == 0) {
         while (ld_acquire_gpu(bar) < target) { }
         // The fence is what invalidates this SM's L1: the other threads' plain loads after the barrier (addends, leaf
         // input) must not hit lines cached before another CTA -- or this CTA's own TMA store, which bypasses L1 --
@@ -314,7 +319,8 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                 if (stored && tid == 0) ptx::bulk_wait_group0();  // this step's tile stores are performed before the barrier
             }
         }
-        grid_step_barrier(a.barrier, (unsigned)G * (unsigned)(s + 1), (prof && s < 61) ? a.dbg_clk + 64 + 3 * s + 2 : nullptr);
+        grid_step_arrive(a.barrier, (prof && s < 61) ? a.dbg_clk + 64 + 3 * s + 2 : nullptr);
+        grid_step_wait(a.barrier, (unsigned)G * (unsigned)(s + 1));
     }
     stamp(a.num_steps, false);
     stamp(a.num_steps + 2, true);

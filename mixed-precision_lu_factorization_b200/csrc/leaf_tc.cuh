@@ -9,9 +9,11 @@
 //      over 16-byte operand chunks (staging, write-back): ~2.5k instructions that stay resident.
 //   2. The O(n^3) parts -- the rank-32 Schur updates (P3: 21k cycles) and the block-recursive merges of the inverses
 //      (I2: 19k cycles) -- were bound by shared-memory bandwidth on the FMA pipe.  Here they are tcgen05.mma products:
-//      fp32 values are split x = h + l into two bf16 parts (16 mantissa bits), a product is h*h + h*l + l*h with fp32
-//      accumulation in TMEM (error ~2^-16 per term, 30x below the 16-bit operand rounding of every product outside the
-//      leaf); operand tiles are staged by all 512 threads in the SWIZZLE_128B layout of gemm_tc.cu's descriptors.
+//      fp32 values are split x = p0 + p1 + p2 into three bf16 parts (24 mantissa bits) and a product is the six part
+//      products of order <= 2 (p0 p0 + p0 p1 + p1 p0 + p0 p2 + p1 p1 + p2 p0) with fp32 accumulation in TMEM: fp32-class
+//      accuracy like the FMA leaf.  (Two parts, 16 bits, were measured first: fine on dominant matrices, but the bf16
+//      operand mode at kappa = 1e6 went from 31 to 114 GMRES steps -- ill-conditioned diagonal blocks need the leaf's
+//      full precision.)  Operand tiles are staged by all 512 threads in the SWIZZLE_128B layout of gemm_tc.cu's descriptors.
 // Two CTAs (one cluster) per block as before: both factor the block, CTA 0 delivers L\U + inv(L11), CTA 1 inv(U11).
 #pragma once
 #include "leaf.cuh"
@@ -27,29 +29,42 @@ struct LeafTc {
 
 // staging region (third 128 x 129 fp32 array of the leaf's shared memory, 1024-byte aligned): operand slabs of up to
 // 128 rows x 128 bytes
-constexpr int TC_A_H = 0, TC_A_L = 16384, TC_B_H = 32768, TC_B_L = 49152;
+// K = 32 operands keep two parts in one 128-byte row [p0(32) | p1(32)] of their first slab (A: +0, B: +32768) and p2 in
+// the first half-rows of their second slab (A: +16384, B: +49152); K = 64 operands and MN-major operands (rows of up to
+// 64 values) use three slabs of 8 KiB (A: +0, +8192, +16384 -- the MMA reads 128 rows, the upper 64 are don't-care rows;
+// B: +32768, +40960, +49152).
+constexpr int TC_A0 = 0, TC_A1 = 8192, TC_A2 = 16384, TC_B0 = 32768, TC_B1 = 40960, TC_B2 = 49152;
 constexpr int TC_STAGE_BYTES = 65536;
 static_assert(TC_STAGE_BYTES <= DB * LDS * 4 && (2 * DB * LDS * 4) % 1024 == 0, "staging area");
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&p);
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // a in the low half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
-// one 16-byte chunk (8 consecutive elements) of tile row `row`: bf16 high parts to chunk ch_h of slab hs, low parts
-// (x - h, rounded to bf16) to chunk ch_l of slab ls; chunk index XOR row%8 inside the 128-byte row (SWIZZLE_128B)
-__device__ __forceinline__ void stage_chunk(uint8_t* hs, uint8_t* ls, int row, int ch_h, int ch_l, const float (&v)[8]) {
-    float h[8], l[8];
+// one 16-byte chunk (8 consecutive elements) of tile row `row` as three bf16 parts: part i to chunk ch[i] of slab sl[i];
+// chunk index XOR row%8 inside the 128-byte row (SWIZZLE_128B)
+struct TcSlabs {
+    uint8_t* sl[3];
+    int ch0[3];  // first chunk of each part inside its slab's rows
+};
+__device__ __forceinline__ void stage_chunk(const TcSlabs& t, int row, int c, const float (&v)[8]) {
+    uint32_t p0[4], p1[4], p2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-        l[i] = v[i] - h[i];
+    for (int i = 0; i < 4; ++i) {
+        p0[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        const float r0 = v[2 * i] - __uint_as_float(p0[i] << 16), r1 = v[2 * i + 1] - __uint_as_float(p0[i] & 0xffff0000u);
+        p1[i] = pack_bf16x2(r0, r1);
+        p2[i] = pack_bf16x2(r0 - __uint_as_float(p1[i] << 16), r1 - __uint_as_float(p1[i] & 0xffff0000u));
     }
-    const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-    *reinterpret_cast<uint4*>(hs + rbase + (((uint32_t)ch_h ^ (uint32_t)(row & 7)) << 4)) =
-        make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    *reinterpret_cast<uint4*>(ls + rbase + (((uint32_t)ch_l ^ (uint32_t)(row & 7)) << 4)) =
-        make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    const uint32_t rbase = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u, x = (uint32_t)(row & 7);
+    *reinterpret_cast<uint4*>(t.sl[0] + rbase + ((((uint32_t)(t.ch0[0] + c)) ^ x) << 4)) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    *reinterpret_cast<uint4*>(t.sl[1] + rbase + ((((uint32_t)(t.ch0[1] + c)) ^ x) << 4)) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(t.sl[2] + rbase + ((((uint32_t)(t.ch0[2] + c)) ^ x) << 4)) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
 }
+// slabs of a K = 32 operand ([p0 | p1] rows + p2 rows) / of a 64-wide or MN-major operand (three slabs) at `base`
+__device__ __forceinline__ TcSlabs slabs32(uint8_t* first, uint8_t* second) { return TcSlabs{{first, first, second}, {0, 4, 0}}; }
+__device__ __forceinline__ TcSlabs slabs3(uint8_t* base, int off = 0) { return TcSlabs{{base + off, base + 8192 + off, base + 16384 + off}, {0, 0, 0}}; }
 
 // An operand element (r, k) = sign * p[r * rs + k * ks], read as zero where the never-written upper-right 32x32 block of
 // a 64x64 triangular matrix would be touched: zmode 1: r < 32 <= k, zmode 2: k < 32 <= r.
@@ -63,11 +78,11 @@ struct TcSrc {
 //   nch == 4 (K = 32): both parts in one slab, row = [h(32) | l(32)]  (pass ls == hs)
 //   nch == 8 (K = 64): parts in two slabs
 struct TcDst {
-    uint8_t *hs, *ls;  // slabs of the high / low parts
-    int nrows, row0;   // operand rows [0, nrows) become tile rows row0 + r
+    TcSlabs slabs;
+    int nrows, row0;  // operand rows [0, nrows) become tile rows row0 + r
 };
 __device__ __forceinline__ void stage_item(const TcDst& d, const TcSrc& s, int nch, int idx) {
-    const int lsh = nch == 4 ? 2 : 3, chl0 = nch == 4 ? 4 : 0;
+    const int lsh = nch == 4 ? 2 : 3;
     const int r = idx >> lsh, c = idx & (nch - 1);
     float v[8];
 #pragma unroll
@@ -76,10 +91,10 @@ __device__ __forceinline__ void stage_item(const TcDst& d, const TcSrc& s, int n
         const bool z = (s.zmode == 1 && r < SB && k >= SB) || (s.zmode == 2 && k < SB && r >= SB);
         v[i] = z ? 0.f : s.sign * s.p[r * s.rs + k * s.ks];
     }
-    stage_chunk(d.hs, d.ls, d.row0 + r, c, chl0 + c, v);
+    stage_chunk(d.slabs, d.row0 + r, c, v);
 }
 // up to two operands in one pass over the CTA's threads (the second starts at a warp boundary of the item space)
-__device__ __noinline__ void stage_tiles(const TcDst d0, const TcSrc s0, const TcDst d1, const TcSrc s1, int nch, int tid) {
+__device__ __forceinline__ void stage_tiles(const TcDst d0, const TcSrc s0, const TcDst d1, const TcSrc s1, int nch, int tid) {
     const int lsh = nch == 4 ? 2 : 3;
     const int n0 = d0.nrows << lsh, n1 = d1.nrows << lsh, n0r = (n0 + 31) & ~31;
 #pragma unroll 1
@@ -87,9 +102,6 @@ __device__ __noinline__ void stage_tiles(const TcDst d0, const TcSrc s0, const T
         if (idx < n0) stage_item(d0, s0, nch, idx);
         else if (idx >= n0r) stage_item(d1, s1, nch, idx - n0r);
     }
-}
-__device__ __forceinline__ void stage_tile(uint8_t* hs, uint8_t* ls, int nrows, int row0, int nch, const TcSrc s, int tid) {
-    stage_tiles(TcDst{hs, ls, nrows, row0}, s, TcDst{hs, ls, 0, 0}, s, nch, tid);
 }
 
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -99,25 +111,33 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "memory");
 }
 
-// D[128 x N] (TMEM, fp32) = A * B over K = 16 * ksteps from the three part products; issued by ONE thread.
-//   A K-major: part h at a_h, part l at a_l (byte addresses of k = 0), 32 bytes per k-step
-//   B K-major (b_mn = false: 32 bytes per k-step) or MN-major (b_mn = true: 16 k-rows = 2048 bytes per k-step)
-__device__ __noinline__ void tc_product(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t b_h, uint32_t b_l, int ksteps,
-                                           bool b_mn, int N) {
-    const uint32_t idesc = make_idesc_f16(128, N, true, false, b_mn);
-    // descriptors of k = 0; a k-step adds to the 16-byte-granular start-address field (bits 0-13) only
-    const uint64_t ah = ptx::make_smem_desc_sw128(a_h, 0, 1024), al = ptx::make_smem_desc_sw128(a_l, 0, 1024);
-    const uint64_t bh = ptx::make_smem_desc_sw128(b_h, b_mn ? 8192u : 0u, 1024), bl = ptx::make_smem_desc_sw128(b_l, b_mn ? 8192u : 0u, 1024);
-    const uint64_t bstep = b_mn ? 128u : 2u;
-    uint32_t acc = 0;
+// Descriptors (k = 0) of the staging area's A and B bases, built once per leaf: a part / k-step / sub-operand is an add
+// to the 16-byte-granular start-address field (descriptor construction by the single issuing thread cost ~1k cycles per
+// product, on the critical path).
+struct TcDesc {
+    uint64_t a, b;  // K-major, no leading-byte offset; MN-major adds kTcMnLbo
+};
+constexpr uint64_t kTcMnLbo = (uint64_t)(8192 >> 4) << 16;
+// D[128 x N] (TMEM, fp32) = A * B over K = 16 * KSTEPS from the six part products of order <= 2, small terms first;
+// issued by ONE thread.  kK32: K = 32 operands in the [p0 | p1] + p2 layout, else three 8 KiB slabs.  B K-major (32 bytes per
+// k-step) or MN-major (kBmn: three slabs, 16 k-rows = 2048 bytes per k-step); b_off: byte offset of a second operand.
+template <int KSTEPS, bool kK32, bool kBmn>
+__device__ __forceinline__ void tc_product(uint32_t d_tmem, const TcDesc& t, uint32_t b_off, int N) {
+    const uint32_t idesc = make_idesc_f16(128, N, true, false, kBmn);
+    uint64_t ap[3], bp[3];
+    ap[0] = t.a;
+    ap[1] = t.a + (kK32 ? 4 : (TC_A1 >> 4));
+    ap[2] = t.a + (TC_A2 >> 4);
+    const uint64_t bb = t.b + (b_off >> 4) + (kBmn ? kTcMnLbo : 0);
+    bp[0] = bb;
+    bp[1] = bb + ((kK32 && !kBmn) ? 4 : ((TC_B1 - TC_B0) >> 4));
+    bp[2] = bb + ((TC_B2 - TC_B0) >> 4);
+    constexpr uint64_t bstep = kBmn ? 128 : 2;
+    constexpr int pa[6] = {2, 1, 0, 1, 0, 0}, pb[6] = {0, 1, 2, 0, 1, 0};
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {  // l*h, h*l, h*h: small terms first
-        const uint64_t ad = pass == 0 ? al : ah, bd = pass == 1 ? bl : bh;
-#pragma unroll 1
-        for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_f16<1>(d_tmem, ad + 2u * k, bd + bstep * k, idesc, acc);
-            acc = 1;
-        }
+    for (int t6 = 0; t6 < 6; ++t6) {
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) ptx::umma_f16<1>(d_tmem, ap[pa[t6]] + 2 * k, bp[pb[t6]] + bstep * k, idesc, (t6 | k) ? 1u : 0u);
     }
 }
 // staged operands -> MMAs (one thread) -> completion, executed by every thread of the CTA
@@ -146,16 +166,23 @@ __device__ __forceinline__ void substitute32(const float (*mt)[SB], const float*
 #pragma unroll 1
     for (int g = 0; g < SB / 8; ++g) {
         const int kb = 8 * g;  // window element i is x[kb + i]
+        float rdg[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) rdg[jj] = scale ? rd[kb + jj] : 1.f;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const int k = kb + jj;
-            if (scale) w[jj] *= rd[k];
+            // window columns beyond 31 are dead: they read on into the next row of mt (one padding row at the end) and
+            // are never stored -- cheaper than a predicate per group on this dependent chain.  Loads first: they do not
+            // depend on the chain.
+            float4 cv[SB / 4];
+#pragma unroll
+            for (int c4 = ((jj + 1) & ~3); c4 < SB; c4 += 4) cv[c4 >> 2] = *reinterpret_cast<const float4*>(&mt[k][kb + c4]);
+            w[jj] *= rdg[jj];
             const float xk = w[jj];
 #pragma unroll
             for (int c4 = ((jj + 1) & ~3); c4 < SB; c4 += 4) {
-                // window columns beyond 31 are dead: they read on into the next row of mt (one padding row at the end)
-                // and are never stored -- cheaper than a predicate per group on this dependent chain
-                const float4 v = *reinterpret_cast<const float4*>(&mt[k][kb + c4]);
+                const float4 v = cv[c4 >> 2];
                 if (c4 > jj) w[c4] = fmaf(-xk, v.x, w[c4]);
                 if (c4 + 1 > jj) w[c4 + 1] = fmaf(-xk, v.y, w[c4 + 1]);
                 if (c4 + 2 > jj) w[c4 + 2] = fmaf(-xk, v.z, w[c4 + 2]);
@@ -192,6 +219,7 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float* Wb = W + k0 + (long long)k0 * ldw;
     if (tid == 0) s_zero = 0;
+    const TcDesc td{ptx::make_smem_desc_sw128(ptx::smem_u32(stage + TC_A0), 0, 1024), ptx::make_smem_desc_sw128(ptx::smem_u32(stage + TC_B0), 0, 1024)};
     {   // lanes -> consecutive rows: coalesced; 8 loads of a thread in flight per round
         const int r = tid & (DB - 1), cq = tid >> 7;
 #pragma unroll 1
@@ -231,6 +259,9 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
                 for (int jj = 0; jj < 8; ++jj) {
                     const int j = cb + jj;
                     const float* prow = s_prow[j & 1];
+                    float4 pv[SB / 4];  // the pivot row's window: loads in flight under the reciprocal chain
+#pragma unroll
+                    for (int c4 = ((jj + 1) & ~3); c4 < SB; c4 += 4) pv[c4 >> 2] = *reinterpret_cast<const float4*>(&prow[cb + c4]);
                     const float piv = prow[j];
                     zp |= (piv == 0.f);
                     const float rp = fast_rcp(piv);
@@ -239,7 +270,7 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
                     w[jj] = (lane > j) ? l : w[jj];
 #pragma unroll
                     for (int c4 = ((jj + 1) & ~3); c4 < SB; c4 += 4) {  // columns beyond 31: dead tail, no predicate
-                        const float4 v = *reinterpret_cast<const float4*>(&prow[cb + c4]);
+                        const float4 v = pv[c4 >> 2];
                         if (c4 > jj) w[c4] = fmaf(-l, v.x, w[c4]);
                         if (c4 + 1 > jj) w[c4 + 1] = fmaf(-l, v.y, w[c4 + 1]);
                         if (c4 + 2 > jj) w[c4 + 2] = fmaf(-l, v.z, w[c4 + 2]);
@@ -297,16 +328,15 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
         // the TMEM lane of a result is its matrix row), B(n, k) = U12(o+k, o+32+n); D = TMEM columns [0, m)
 #define SUB_CLK(i) do { if (dbg_clk && threadIdx.x == 0 && kb == 1) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); dbg_clk[40 + (i)] = t_; } } while (0)
         SUB_CLK(0);
-        stage_tiles(TcDst{stage + TC_A_H, stage + TC_A_H, m, o + SB}, TcSrc{S + (o + SB) + o * LDS, 1, LDS, -1.f, 0},
-                    TcDst{stage + TC_B_H, stage + TC_B_H, m, 0}, TcSrc{S + o + (o + SB) * LDS, LDS, 1, 1.f, 0}, 4, tid);
+        stage_tiles(TcDst{slabs32(stage + TC_A0, stage + TC_A2), m, o + SB}, TcSrc{S + (o + SB) + o * LDS, 1, LDS, -1.f, 0},
+                    TcDst{slabs32(stage + TC_B0, stage + TC_B2), m, 0}, TcSrc{S + o + (o + SB) * LDS, LDS, 1, 1.f, 0}, 4, tid);
         SUB_CLK(1);
         ptx::fence_proxy_async();
         __syncthreads();
         SUB_CLK(2);
         if (threadIdx.x == 0) {
             ptx::tc_fence_after();
-            const uint32_t ab = ptx::smem_u32(stage + TC_A_H), bb = ptx::smem_u32(stage + TC_B_H);
-            tc_product(tc.tmem, ab, ab + 64, bb, bb + 64, 2, false, m);
+            tc_product<2, true, false>(tc.tmem, td, 0, m);
             ptx::umma_commit<1>(tc.bar);
         }
         SUB_CLK(3);
@@ -339,22 +369,30 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
     }
     __syncthreads();
     DBG_CLK();
+    // The L\U block is final: CTA 0 sends it off now, so that its 64 KiB of stores drain under the merges below instead of
+    // in front of the step barrier's release (measured: the drain, not the issue, is what a leaf waits for while the bulk
+    // lane keeps L2 busy).
+    if (which == 0) {
+        const int r = tid & (DB - 1), cq = tid >> 7;
+#pragma unroll 4
+        for (int i = 0; i < DB / 4; ++i) Wb[r + (long long)(cq + 4 * i) * ldw] = S[r + (cq + 4 * i) * LDS];
+    }
 
     // ---- I2: off-diagonal blocks of this CTA's inverse by block-recursive doubling (32 -> 64 -> 128) on the tensor
     // cores.  M(r, k) = the factor read as lower triangular: L11(r, k), or U11^T(r, k) = U11(k, r).
     {
         const int mrs = which ? LDS : 1, mks = which ? 1 : LDS;  // M(r, k) = S[r * mrs + k * mks]
         const int q = warp & 3, part = warp >> 2;
-        uint8_t *ah = stage + TC_A_H, *al = stage + TC_A_L, *bh = stage + TC_B_H, *bl = stage + TC_B_L;
+        const TcSlabs a32 = slabs32(stage + TC_A0, stage + TC_A2), b32 = slabs32(stage + TC_B0, stage + TC_B2);
+        const TcSlabs a64 = slabs3(stage + TC_A0), b64 = slabs3(stage + TC_B0);
         // level 1, both 64x64 problems (d = 0, 64) at once.  T_d = M21_d X11_d: matrix rows d+32 .. d+63 (= tile rows), K = N = 32
-        stage_tiles(TcDst{ah, ah, SB, SB}, TcSrc{S + SB * mrs, mrs, mks, 1.f, 0},
-                    TcDst{ah, ah, SB, 64 + SB}, TcSrc{S + (64 + SB) * mrs + 64 * mks, mrs, mks, 1.f, 0}, 4, tid);
-        stage_tiles(TcDst{bh, bh, SB, 0}, TcSrc{Xh, LDS, 1, 1.f, 0},                        // B(n, k) = X11_0(k, n)
-                    TcDst{bh, bh, SB, SB}, TcSrc{Xh + 64 + 64 * LDS, LDS, 1, 1.f, 0}, 4, tid);  // rows 32..63: X11_64
+        stage_tiles(TcDst{a32, SB, SB}, TcSrc{S + SB * mrs, mrs, mks, 1.f, 0},
+                    TcDst{a32, SB, 64 + SB}, TcSrc{S + (64 + SB) * mrs + 64 * mks, mrs, mks, 1.f, 0}, 4, tid);
+        stage_tiles(TcDst{b32, SB, 0}, TcSrc{Xh, LDS, 1, 1.f, 0},                        // B(n, k) = X11_0(k, n)
+                    TcDst{b32, SB, SB}, TcSrc{Xh + 64 + 64 * LDS, LDS, 1, 1.f, 0}, 4, tid);  // rows 32..63: X11_64
         LEAF_TC_ISSUE_BEGIN()
-            const uint32_t ab = ptx::smem_u32(ah), bb = ptx::smem_u32(bh);
-            tc_product(tc.tmem + 0, ab, ab + 64, bb, bb + 64, 2, false, 32);                 // rows 32..63 are T_0
-            tc_product(tc.tmem + 32, ab, ab + 64, bb + 4096, bb + 4096 + 64, 2, false, 32);  // rows 96..127 are T_64
+            tc_product<2, true, false>(tc.tmem + 0, td, 0, 32);      // rows 32..63 are T_0
+            tc_product<2, true, false>(tc.tmem + 32, td, 4096, 32);  // rows 96..127 are T_64
         LEAF_TC_ISSUE_END(tc)
         // X21_d = -X22_d T_d.  T comes back through TMEM lane quarters 1 and 3, 8 columns per warp = one 16-byte chunk of
         // the MN-major B slabs (row = k); the MMAs that read the slabs have completed (the wait above)
@@ -366,15 +404,14 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d[j]);
-            stage_chunk(bh + so, bl + so, lane, part, part, v);
+            stage_chunk(slabs3(stage + TC_B0, so), lane, part, v);
         }
-        stage_tiles(TcDst{ah, ah, SB, SB}, TcSrc{Xh + SB + SB * LDS, 1, LDS, -1.f, 0},                          // A(r, k) = -X22_0
-                    TcDst{ah, ah, SB, 64 + SB}, TcSrc{Xh + (64 + SB) + (64 + SB) * LDS, 1, LDS, -1.f, 0}, 4, tid);  //           -X22_64
+        stage_tiles(TcDst{a32, SB, SB}, TcSrc{Xh + SB + SB * LDS, 1, LDS, -1.f, 0},                          // A(r, k) = -X22_0
+                    TcDst{a32, SB, 64 + SB}, TcSrc{Xh + (64 + SB) + (64 + SB) * LDS, 1, LDS, -1.f, 0}, 4, tid);  //           -X22_64
         ptx::tc_fence_before();
         LEAF_TC_ISSUE_BEGIN()
-            const uint32_t ab = ptx::smem_u32(ah), bhh = ptx::smem_u32(bh), bll = ptx::smem_u32(bl);
-            tc_product(tc.tmem + 64, ab, ab + 64, bhh, bll, 2, true, 32);
-            tc_product(tc.tmem + 96, ab, ab + 64, bhh + 4096, bll + 4096, 2, true, 32);
+            tc_product<2, true, true>(tc.tmem + 64, td, 0, 32);
+            tc_product<2, true, true>(tc.tmem + 96, td, 4096, 32);
         LEAF_TC_ISSUE_END(tc)
         if (q == 1 || q == 3) {
             const int d0 = q == 3 ? 64 : 0, r = q * 32 + lane;
@@ -388,10 +425,10 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
         __syncthreads();  // X21 of both 64x64 blocks is in Xh
         // level 2: T = M21 X11 (matrix rows 64..127 as tile rows 0..63, K = N = 64); the upper-right 32x32 blocks of the
         // 64x64 triangular operands were never written and are read as zero
-        stage_tiles(TcDst{ah, al, 64, 0}, TcSrc{S + 64 * mrs, mrs, mks, 1.f, 0},
-                    TcDst{bh, bl, 64, 0}, TcSrc{Xh, LDS, 1, 1.f, 2}, 8, tid);  // B(n, k) = X11(k, n): zero for k < 32 <= n
+        stage_tiles(TcDst{a64, 64, 0}, TcSrc{S + 64 * mrs, mrs, mks, 1.f, 0},
+                    TcDst{b64, 64, 0}, TcSrc{Xh, LDS, 1, 1.f, 2}, 8, tid);  // B(n, k) = X11(k, n): zero for k < 32 <= n
         LEAF_TC_ISSUE_BEGIN()
-            tc_product(tc.tmem + 0, ptx::smem_u32(ah), ptx::smem_u32(al), ptx::smem_u32(bh), ptx::smem_u32(bl), 4, false, 64);
+            tc_product<4, false, false>(tc.tmem + 0, td, 0, 64);
         LEAF_TC_ISSUE_END(tc)
         if (q < 2) {  // T row k = TMEM lane = tile row; 2 x 8 of its 64 columns per warp -> chunks of the MN-major B slabs
 #pragma unroll 1
@@ -402,13 +439,13 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(d[j]);
-                stage_chunk(bh, bl, q * 32 + lane, hh * 4 + part, hh * 4 + part, v);
+                stage_chunk(b64, q * 32 + lane, hh * 4 + part, v);
             }
         }
-        stage_tile(ah, al, 64, 0, 8, TcSrc{Xh + 64 + 64 * LDS, 1, LDS, -1.f, 1}, tid);  // A(i, k) = -X22(i, k): zero for i < 32 <= k
+        stage_tiles(TcDst{a64, 64, 0}, TcSrc{Xh + 64 + 64 * LDS, 1, LDS, -1.f, 1}, TcDst{a64, 0, 0}, TcSrc{Xh, 1, 1, 1.f, 0}, 8, tid);  // A(i, k) = -X22(i, k): zero for i < 32 <= k
         ptx::tc_fence_before();
         LEAF_TC_ISSUE_BEGIN()
-            tc_product(tc.tmem + 64, ptx::smem_u32(ah), ptx::smem_u32(al), ptx::smem_u32(bh), ptx::smem_u32(bl), 4, true, 64);
+            tc_product<4, false, true>(tc.tmem + 64, td, 0, 64);
         LEAF_TC_ISSUE_END(tc)
         if (q < 2) {
             const int i = q * 32 + lane;
@@ -453,7 +490,8 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
         sI = tile_scales[2 * which];
     }
 
-    // ---- write back (as leaf.cuh): CTA 0 the W block (L\U) and inv(L11), CTA 1 inv(U11); triangles only
+    // ---- write back: the scaled 16-bit inverse into the band and its fp32 copy for the triangular solves (triangles
+    // only: the other halves stay zero).  The L\U block itself left right after the elimination loop (see there).
     uint16_t* I16 = reinterpret_cast<uint16_t*>(which ? Uinv16 : Linv16);
     float* I32 = which ? Uinv32 : Linv32;
     if (I32) I32 += (long long)blk * DB * DB;
@@ -465,7 +503,6 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
         for (int i = 0; i < DB / 4; ++i) {
             const int c = cq + 4 * i;
             if (which == 0) {
-                Wb[r + (long long)c * ldw] = S[r + c * LDS];
                 if (r >= c) {
                     const float xl = Xh[r + c * LDS];  // inv(L11)(r,c)
                     float v = xl * sI;
@@ -474,7 +511,7 @@ __device__ __forceinline__ void diag_lu_body_tc(float* dl_smem, const int which,
                     if (I32) I32[r + c * DB] = xl;
                 }
             } else if (r <= c) {
-                const float zu = Xh[c + r * LDS];  // inv(U11)(r,c) = inv(U11^T)(c,r)
+                const float zu = Xh[c + r * LDS];      // inv(U11)(r,c) = inv(U11^T)(c,r)
                 float v = zu * sI;
                 if (c < valid) mx = fmaxf(mx, fabsf(v)); else v = fminf(fmaxf(v, -PADMAX), PADMAX);
                 store16(I16, r + (long long)c * ld16, v, bf16);

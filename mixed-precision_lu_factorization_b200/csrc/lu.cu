@@ -511,7 +511,7 @@ struct Sched {
             if ((int)c->fprof_prog.size() <= li) c->fprof_prog.resize(li + 1, -1);
             c->fprof_prog[li] = (int)(fp - c->fprogs.data());
         }
-        int G = c->opts.fuse_ctas > 0 ? c->opts.fuse_ctas : 16;
+        int G = c->opts.fuse_ctas > 0 ? c->opts.fuse_ctas : 8;
         const int budget = lane_sms(c, ln);
         if (G > budget) G = budget;
         G -= G % 2;
@@ -853,7 +853,7 @@ int enqueue_factorization_left(mplu_context* c) {
     const int nt = (npad + NB - 1) / NB;
     if (nt >= mplu_context::kMaxSteps) return MPLU_E_ARG;
     cudaStream_t st = c->stream;
-    int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 32;
+    int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 24;
     side_sms -= side_sms % 2;
     const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && nt > 2;
     const Lane all{st, 0};
@@ -1331,12 +1331,12 @@ void mplu_default_options(mplu_options* o) {
     o->tri_skip = 1;
     o->stream_host = 1;
     o->schedule = MPLU_SCHED_LEFT;
-    o->side_sms_left = 32;
+    o->side_sms_left = 24;
     o->eager = 1;
     o->stream_c = 1;
     o->early_scale = 0;
-    o->fuse_w = 2048;
-    o->fuse_ctas = 16;
+    o->fuse_w = 512;
+    o->fuse_ctas = 8;
     o->lazy_touch = 1;
 }
 

@@ -121,7 +121,8 @@ def test_config4_kappa_sweep_n16384(mplu, solver, kappa):
             assert st.iters <= it + max(2, it // 3), (kappa, prec, st.iters, it)
             assert st.backward_error <= max(10 * be64, 2 * n * EPS)
         else:
-            assert st.iters == 30 and st.backward_error > 1e-9  # stagnation is reported, not hidden
+            # stagnation (30 iterations) or divergence (stopped early on a non-finite residual) is reported, not hidden
+            assert st.iters <= 30 and not (st.backward_error <= 1e-9)
         xg, sg = solver.gesv(A.t(), b, mplu.default_options(precision=prec, refinement=mplu.REFINE_GMRES), allow_noconv=True)
         go, gk = want["gmres"]
         assert sg.converged == 1, (kappa, prec, sg.as_dict())

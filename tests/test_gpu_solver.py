@@ -172,16 +172,16 @@ def test_early_scale_option(mplu, oracle, solver):
     A = oracle.counter_matrix(n, seed=5)
     A[:, nb:] *= 64.0
     b = A.sum(axis=1)
-    x1, st1 = run(mplu, solver, A, b, nb=nb, early_scale=1)
-    x0, st0 = run(mplu, solver, A, b, nb=nb, early_scale=0)
+    x1, st1 = run(mplu, solver, A, b, nb=nb, early_scale=1, lazy_touch=0)  # (the lazy first touch has its own test)
+    x0, st0 = run(mplu, solver, A, b, nb=nb, early_scale=0, lazy_touch=0)
     assert st0["converged"] == 1 and st0["status_bits"] == 0 and st0["precision_used"] == mplu.MPLU_FP16
     assert st1["converged"] == 1
     np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-11)
     np.testing.assert_allclose(x1, 1.0, rtol=0, atol=1e-10)
     # same matrix without the jump in magnitude: both scale choices are the same power of two, same factors
     A2 = oracle.counter_matrix(n, seed=5)
-    xa, sa = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=1)
-    xb, sb = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=0)
+    xa, sa = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=1, lazy_touch=0)
+    xb, sb = run(mplu, solver, A2, A2.sum(axis=1), nb=nb, early_scale=0, lazy_touch=0)
     assert sa["status_bits"] == 0 and sb["status_bits"] == 0
     np.testing.assert_array_equal(xa, xb)
 
@@ -321,7 +321,7 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
             dict(schedule=0, tile_ws=1), dict(schedule=0, side_sms=16, side_sms_early=8), dict(schedule=0, pdl=2))
         left = tuple(dict(schedule=1, **kw) for kw in common) + (
             dict(schedule=1, eager=0), dict(schedule=1, use_graph=0, side_sms_left=64), dict(schedule=1, side_sms_left=16),
-            dict(schedule=1, early_scale=1), dict(schedule=1, early_scale=1, use_graph=0))
+            dict(schedule=1, early_scale=1, lazy_touch=0), dict(schedule=1, early_scale=1, lazy_touch=0, use_graph=0))
         for kw in right + left:
             x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
             LU = s.factors(n)
@@ -344,8 +344,8 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
     """opts.fuse_w: the GETRF of a diagonal block (leaves + every product between them) as ONE persistent launch with grid
     barriers between the steps (csrc/getrf_fused.cu) instead of one launch per leaf / product group.  The products
     between the leaves are the same tcgen05 products on the same 16-bit operands in the same order; inside a leaf the
-    fused kernel forms the rank-32 updates and the inverse merges on the tensor cores from two-part bf16 splits (2^-16
-    per term) where the stand-alone leaf uses fp32 FMAs, so the factors agree to that level, not bit for bit; fused runs
+    fused kernel forms the rank-32 updates and the inverse merges on the tensor cores from three-part bf16 splits (fp32-class
+    accuracy, another summation order) where the stand-alone leaf uses fp32 FMAs, so the factors agree to rounding level, not bit for bit; fused runs
     agree with each other bit for bit.  nb = 4096 exercises the step program read from global memory (it does not fit the
     shared-memory staging area), n = 3000 the identity padding."""
     import torch
@@ -366,7 +366,8 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
         dU = (torch.triu(LU1) - torch.triu(LU0)).abs().max().item()
         dL = (torch.tril(LU1, -1) - torch.tril(LU0, -1)).abs().max().item()
         assert dU <= 1e-5 * LU0.abs().max().item(), dU  # a few dozen fp32 ulps of the diagonal: the summation order differs
-        assert dL <= 1e-4 * torch.tril(LU0, -1).abs().max().item(), dL
+        # the 16-bit inverse of a diagonal block can round the other way: one fp16 ulp of a multiplier
+        assert dL <= (2.0 ** -10 if precision == 0 else 2.0 ** -7) * torch.tril(LU0, -1).abs().max().item(), dL
         assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
     finally:
         s.close()
