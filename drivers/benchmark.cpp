@@ -4,10 +4,16 @@
 // same input format (count, then n and n*n values consumed sequentially as column-major storage, :186-194), same
 // check (P*L*U == A element-wise, absolute tolerance 1e-10, :97-144) and the same CSV, "benchmark_times.csv" with
 // header matrix_size,mpf_time,lapack_time and 10 fixed decimals (:168-169,265).
+// and the same stdout lines and exit codes on that default path (:150,:226,:236; -1 on a bad command line / file).
 // New, behind flags only:
 //     --solve        also solve A x = A*1 with the mixed-precision LU + iterative refinement (mplu_gesv_host) and
-//                    append the columns mplu_time,iters,backward_error to the CSV
+//                    append the columns mplu_time,iters,backward_error,mplu_tflops to the CSV
 //     --csv path     write the CSV somewhere else
+//     --bin          `filename` is binary: int32 count, then per matrix int32 n and n*n float64 values (column-major):
+//                    the text format costs ~20 bytes and a strtod per value, which keeps n = 32768 out of reach
+//     --gen dd:N[:SEED]   no input file at all: the column-dominant synthetic system of mplu_generate (the reference
+//                    generator's value set) is built ON THE DEVICE and solved there (mplu_gesv_device); MPF() and LAPACK
+//                    are skipped (their columns are nan).  `benchmark --gen dd:32768 --solve` reproduces the headline.
 // Host LAPACK/CBLAS are loaded at run time (dlopen) so the driver builds without lapacke.h: MPLU_LAPACK_LIB or the
 // library path baked in at build time (scipy's OpenBLAS in this image, symbols prefixed scipy_); when none is found
 // the lapack_time column is nan and products fall back to a plain triple loop.
@@ -55,6 +61,27 @@ void load_host_blas() {
     }
 }
 
+// the L / U dump of the reference's print_LU (benchmark.cpp:27-57)
+void show_factors(const double* lu, int n, bool verbose) {
+    if (!verbose || n >= 10) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        std::cout << (pass == 0 ? "L matrix:" : "U matrix:") << std::endl;
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) {
+                if (pass == 0) {
+                    if (i > j) std::cout << lu[(size_t)j * n + i] << " ";
+                    else std::cout << (i == j ? "1 " : "0 ");
+                } else {
+                    if (i <= j) std::cout << lu[(size_t)j * n + i] << " ";
+                    else std::cout << "0 ";
+                }
+            }
+            std::cout << std::endl;
+        }
+        std::cout << std::endl;
+    }
+}
+
 void show_matrix(const char* title, const double* a, int n, bool verbose) {
     if (!verbose || n >= 10) return;
     std::cout << title << std::endl;
@@ -91,6 +118,7 @@ void product_of_factors(const double* lu, double* c, int n) {
 // P*L*U == A ?  (swaps applied last to first, as the reference's row_permute)
 bool factors_reproduce(const double* a, const double* lu, const int* ipiv, int n, bool verbose) {
     std::vector<double> plu((size_t)n * n);
+    show_factors(lu, n, verbose);
     product_of_factors(lu, plu.data(), n);
     show_matrix("LU matrix:", plu.data(), n, verbose);
     for (int i = n - 1; i >= 0; --i) {
@@ -109,52 +137,112 @@ double seconds_since(std::chrono::high_resolution_clock::time_point t0) {
     return std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
 }
 
+// LU+IR of the synthetic system generated on the device (no host copy of A at all)
+int run_generated(const std::string& spec, const std::string& csv_path) {
+    int n = 0;
+    unsigned long long seed = 1;
+    if (std::sscanf(spec.c_str(), "dd:%d:%llu", &n, &seed) < 1 || n <= 0) {
+        std::cout << "Invalid --gen spec " << spec << " (dd:N[:SEED])" << std::endl;
+        return -1;
+    }
+    mplu_context* ctx = nullptr;
+    if (mplu_create(&ctx, 0) != 0) {
+        std::cout << "mplu: no CUDA device" << std::endl;
+        return -1;
+    }
+    double *dA = nullptr, *db = nullptr, *dx = nullptr;
+    if (mplu_device_alloc((void**)&dA, (size_t)n * n * sizeof(double)) != 0 || mplu_device_alloc((void**)&db, n * sizeof(double)) != 0 ||
+        mplu_device_alloc((void**)&dx, n * sizeof(double)) != 0 || mplu_generate(n, seed, 1, dA, n, db, mplu_stream(ctx)) != 0) {
+        std::cout << "mplu: device allocation / generation failed for n = " << n << std::endl;
+        return -1;
+    }
+    mplu_stats st;
+    int rc = 0;
+    double best = 1e30;
+    for (int rep = 0; rep < 4 && (rc == 0 || rc == MPLU_E_NOCONV); ++rep) {  // the first call captures the schedule
+        rc = mplu_gesv_device(ctx, n, dA, n, db, dx, nullptr, &st);
+        if (rep > 0 && st.total_ms * 1e-3 < best) best = st.total_ms * 1e-3;
+    }
+    std::ofstream csv(csv_path);
+    csv << "matrix_size,mpf_time,lapack_time,mplu_time,iters,backward_error,mplu_tflops\n" << std::fixed << std::setprecision(10);
+    if (rc != 0 && rc != MPLU_E_NOCONV) {
+        std::cout << "mplu_gesv_device failed with code " << rc << std::endl;
+        return -1;
+    }
+    std::vector<double> x(n);
+    mplu_device_to_host(x.data(), dx, n * sizeof(double));
+    double err = 0.0;
+    for (int i = 0; i < n; ++i) err = std::fmax(err, std::fabs(x[i] - 1.0));
+    const double tflops = 2.0 / 3.0 * (double)n * n * n / best / 1e12;
+    std::cout << "Matriz tamanyo: " << n << std::endl;
+    std::cout << "mplu LU+IR (device-resident, generated dd seed " << seed << "): " << best << " s = " << tflops << " TFLOP/s, " << st.iters
+              << " refinement iterations, backward error " << std::scientific << st.backward_error << ", max|x-1| " << err
+              << std::defaultfloat << (rc ? "  (did not converge)" : "") << std::endl;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    csv << n << "," << nan << "," << nan << "," << best << "," << st.iters << "," << std::scientific << st.backward_error << std::fixed
+        << "," << tflops << std::endl;
+    mplu_device_free(dA); mplu_device_free(db); mplu_device_free(dx);
+    mplu_destroy(ctx);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
-    if (argc < 2) {
-        std::cout << "Usage: " << argv[0] << " filename [-v] [--no-check] [--solve] [--csv path]" << std::endl;
-        return 1;
-    }
-    bool verbose = false, check = true, solve = false;
-    std::string csv_path = "benchmark_times.csv";
-    for (int i = 2; i < argc; ++i) {
+    bool verbose = false, check = true, solve = false, binary = false;
+    std::string csv_path = "benchmark_times.csv", gen;
+    for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "-v") verbose = true;
         else if (a == "--no-check") check = false;
         else if (a == "--solve") solve = true;
+        else if (a == "--bin") binary = true;
         else if (a == "--csv" && i + 1 < argc) csv_path = argv[++i];
+        else if (a == "--gen" && i + 1 < argc) gen = argv[++i];
     }
-    std::ifstream in(argv[1]);
+    if (!gen.empty()) return run_generated(gen, csv_path);
+    if (argc < 2 || argv[1][0] == '-') {
+        std::cout << "Usage: " << argv[0] << " filename [-v] [--no-check]   (also: [--solve] [--bin] [--csv path] | --gen dd:N[:SEED])" << std::endl;
+        return -1;
+    }
+    std::ifstream in(argv[1], binary ? std::ios::binary : std::ios::in);
     if (!in.is_open()) {
         std::cout << "Failed to open " << argv[1] << std::endl;
-        return 1;
+        return -1;
     }
+    auto read_int = [&](int& v) -> bool {
+        if (binary) { int32_t t = 0; in.read(reinterpret_cast<char*>(&t), sizeof(t)); v = t; return (bool)in; }
+        return (bool)(in >> v);
+    };
     load_host_blas();
     std::ofstream csv(csv_path);
-    csv << "matrix_size,mpf_time,lapack_time" << (solve ? ",mplu_time,iters,backward_error" : "") << "\n"
+    csv << "matrix_size,mpf_time,lapack_time" << (solve ? ",mplu_time,iters,backward_error,mplu_tflops" : "") << "\n"
         << std::fixed << std::setprecision(10);
     int count = 0;
-    if (!(in >> count) || count <= 0) {
+    if (!read_int(count) || count <= 0) {
         std::cout << "Invalid number of matrices in " << argv[1] << std::endl;
-        return 1;
+        return -1;
     }
     if (verbose) std::cout << "Number of matrices: " << count << std::endl;
     mplu_context* ctx = nullptr;
 
     for (int m = 0; m < count; ++m) {
         int n = 0;
-        if (!(in >> n) || n <= 0) {
+        if (!read_int(n) || n <= 0) {
             std::cout << "Invalid matrix size in " << argv[1] << " n: " << n << std::endl;
-            return 1;
+            return -1;
         }
         const size_t nn = (size_t)n * n;
         std::vector<double> a(nn);
-        for (size_t e = 0; e < nn; ++e)
-            if (!(in >> a[e])) {
-                std::cout << "Error while reading matrix data in " << argv[1] << std::endl;
-                return 1;
-            }
+        if (binary) {
+            in.read(reinterpret_cast<char*>(a.data()), (std::streamsize)(nn * sizeof(double)));
+        } else {
+            for (size_t e = 0; e < nn && in; ++e) in >> a[e];
+        }
+        if (!in) {
+            std::cout << "Error while reading matrix data in " << argv[1] << std::endl;
+            return -1;
+        }
         show_matrix("Original matrix:", a.data(), n, verbose);
         std::vector<double> w(a);
         std::vector<int> ipiv(n);
@@ -165,11 +253,11 @@ int main(int argc, char** argv) {
         const double mpf_time = seconds_since(t0);
         if (verbose) std::cout << "MPF() time: " << mpf_time << " seconds\n" << std::endl;
         if (check) {
-            if (verbose) std::cout << "Checking correctness of MPF results..." << std::endl;
+            std::cout << "Checking correctness of MPF results..." << std::endl;
             if (!factors_reproduce(a.data(), w.data(), ipiv.data(), n, verbose))
                 std::cout << "MPF produced incorrect results." << std::endl;
         }
-        std::cout << "Matrix size: " << n << std::endl;
+        std::cout << "Matriz tamanyo: " << n << std::endl;  // sic: the reference's line (benchmark.cpp:236)
 
         double lapack_time = std::numeric_limits<double>::quiet_NaN();
         if (g_blas.dgetrf) {
@@ -210,7 +298,8 @@ int main(int argc, char** argv) {
             } else {
                 std::cout << "mplu: no CUDA device" << std::endl;
             }
-            csv << "," << mplu_time << "," << iters << "," << std::scientific << be << std::fixed;
+            csv << "," << mplu_time << "," << iters << "," << std::scientific << be << std::fixed << ","
+                << 2.0 / 3.0 * (double)n * n * n / mplu_time / 1e12;
         }
         csv << std::endl;
     }

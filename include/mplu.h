@@ -187,6 +187,12 @@ int mplu_dgetf2_npv(int m, int n, double *d_panel, int ld, void *stream);
  * off-diagonal sum + 1.  db (optional) receives b = A * ones. */
 int mplu_generate(int n, unsigned long long seed, int dominant, double *dA, long long lda, double *db, void *stream);
 
+/* Device memory for callers that do not link the CUDA runtime themselves (drivers/benchmark.cpp --gen): plain cudaMalloc /
+ * cudaFree / synchronous device-to-host cudaMemcpy on the current device. */
+int mplu_device_alloc(void **ptr, unsigned long long bytes);
+int mplu_device_free(void *ptr);
+int mplu_device_to_host(void *dst, const void *src, unsigned long long bytes);
+
 /* ---- 2D block-cyclic solver across the GPUs of one box (the reference is single-GPU,
  * MPF.cu:77).  The n x n matrix is cut into nb x nb tiles, tile (I,J) lives on process (I mod P, J mod Q) of a
  * P x Q grid, each process stores its tiles in ScaLAPACK local order (column-major mloc x nloc).  One process per

@@ -195,7 +195,9 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
             if (warp == F_EPI_WARPS) {
                 // ------------------------------------------------------------ TMA producer
                 if (lane == 0) {
+                    if (prof && s < 61) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[384 + 4 * s] = t_; }
                     fence_proxy_async_all();  // the previous step's generic-proxy stores (made visible by the barrier) -> TMA
+                    if (prof && s < 61) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[384 + 4 * s + 1] = t_; }
                     for (int t = slot0; t < ntiles; t += G) {
                         const TileRef r = tile_ref(st, probs, t);
                         const FusedProblem& p = *r.p;
@@ -228,6 +230,7 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                     for (int kb = r.kb0; kb < r.kb1; ++kb) {
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
+                        if (prof && lane == 0 && s < 61 && t == 0 && kb == r.kb0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[384 + 4 * s + 2] = t_; }
                         if (lane == 0) {
                             const uint32_t a_base = ptx::smem_u32(sA + stage * F_A_BYTES);
                             const uint32_t b_base = ptx::smem_u32(sB + stage * F_B_BYTES);
@@ -241,6 +244,7 @@ getrf_fused_kernel(const __grid_constant__ FusedMaps maps, const FusedArgs a) {
                             }
                             ptx::umma_commit<1>(&empty[stage]);
                             if (kb == r.kb1 - 1) ptx::umma_commit<1>(&tfull[as]);
+                            if (prof && s < 61 && t == 0 && kb == r.kb1 - 1) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); a.dbg_clk[384 + 4 * s + 3] = t_; }
                         }
                         __syncwarp();
                         if (++stage == FSTAGES) { stage = 0; phase ^= 1; }

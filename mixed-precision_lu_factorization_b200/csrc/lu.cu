@@ -1709,6 +1709,21 @@ int mplu_debug_trace(int n, int nb, const mplu_options* opts, int* out, int max)
     return (int)pos;
 }
 
+int mplu_device_alloc(void** ptr, unsigned long long bytes) {
+    if (!ptr) return MPLU_E_ARG;
+    CK(cudaMalloc(ptr, (size_t)bytes));
+    return 0;
+}
+int mplu_device_free(void* ptr) {
+    CK(cudaFree(ptr));
+    return 0;
+}
+int mplu_device_to_host(void* dst, const void* src, unsigned long long bytes) {
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // sizes of the interface structs, so that a binding (ctypes, cgo, JNI) can check its mirror of include/mplu.h
 int mplu_sizeof_options(void) { return (int)sizeof(mplu_options); }
 int mplu_sizeof_stats(void) { return (int)sizeof(mplu_stats); }
@@ -1805,6 +1820,17 @@ int mplu_debug_fused_profile(mplu_context* c, int launch, long long* out, int ma
         ++nrec;
     }
     return nrec;
+}
+
+// the raw time-stamp slots of fused launch `launch` (layout: see getrf_fused.cu / tools/fused_profile.py)
+int mplu_debug_fused_raw(mplu_context* c, int launch, long long* out, int max_slots) {
+    if (!c || !out || !c->fprof || launch < 0 || launch >= c->fbar_cap) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    const int k = max_slots < mplu_context::kFusedProfSlots ? max_slots : mplu_context::kFusedProfSlots;
+    if (cudaMemcpy(out, c->fprof + (size_t)launch * mplu_context::kFusedProfSlots, (size_t)k * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 0;
+    return k;
 }
 
 int mplu_residual(int n, const double* dA, long long lda, const double* dx, const double* db, double* dr,

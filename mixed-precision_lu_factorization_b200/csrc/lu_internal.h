@@ -81,7 +81,7 @@ struct mplu_context {
     int fbar_cap = 0, fbar_next = 0;
     // development aid (mplu_debug_fused_profile): per fused launch of the last factorization, which program it ran and
     // a slice of kFusedProfSlots time stamps
-    static constexpr int kFusedProfSlots = 384;
+    static constexpr int kFusedProfSlots = 640;
     long long* fprof = nullptr;
     bool fprof_on = false, fprof_sub = false;
     std::vector<int> fprof_prog;  // launch index -> index into fprogs

@@ -15,6 +15,7 @@ which = [int(x) for x in kv.pop("launches", "0,5").split(",")]
 lib = m.load_library()
 lib.mplu_debug_fused_profile_enable.argtypes = [C.c_void_p, C.c_int]
 lib.mplu_debug_fused_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.c_int]
+lib.mplu_debug_fused_raw.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong), C.c_int]
 s = m.Solver(0)
 A, b = m.generate(n, seed=1)
 opts = m.default_options(nb=nb, **{k: int(v) for k, v in kv.items()})
@@ -36,13 +37,21 @@ for li in which:
     end_clk, wall_ns = rec[-1][3], rec[-1][2]
     tot = end_clk - rec[0][3]
     print(f"launch {li}: {k - 1} steps, {tot} cycles, {wall_ns / 1e3:.1f} us wall = {tot / max(wall_ns, 1) * 1e3:.0f} MHz")
+    raw = (C.c_longlong * 640)()
+    nraw = lib.mplu_debug_fused_raw(s._ctx, li, raw, 640)
     summ = {}
+    prod = {}
     for i in range(k - 1):
         kind, tiles, kk, clk = rec[i]
         sub = ((tiles >> 20) & 0xFFFFF, (tiles >> 40) & 0xFFFFF, (kk >> 20) & 0xFFFFF)  # tfull, epilogue done, barrier entered (CTA 0)
         tiles &= 0xFFFFF; kk &= 0xFFFFF
         dur = (rec[i + 1][3] if i + 1 < k - 1 else end_clk) - clk
         key = "leaf" if kind == 1 else f"gemm K={kk} tiles={tiles}"
+        if nraw >= 384 + 4 * i + 4 and kind == 0 and i < 61:
+            p = prod.setdefault(key, [0, 0, 0, 0, 0])
+            p[0] += 1
+            for q in range(4):
+                p[1 + q] += max(0, min(raw[384 + 4 * i + q] - clk, 1 << 20))
         a = summ.setdefault(key, [0, 0, 0, 0, 0])
         a[0] += 1; a[1] += dur; a[2] += sub[0]; a[3] += sub[1]; a[4] += sub[2]
         if "verbose" in kv or k <= 40:
@@ -58,6 +67,8 @@ for li in which:
             print("   P3 (kb=1) on the tensor cores: " + " ".join(f"{nm}={sub[i + 1] - sub[i]}" for i, nm in enumerate(["stage", "fence+sync", "issue+commit", "wait", "TMEM->S+sync"])))
         d = [leafclk[i + 1] - leafclk[i] for i in range(len(leafclk) - 1) if leafclk[i + 1] > 0]
         print("   last leaf phases (cycles): " + " ".join(f"{nm}={v}" for nm, v in zip(names, d)))
+    for key, (cnt, p0, p1, p2, p3) in prod.items():
+        print(f"   {key:28s} first tile: producer awake @{p0 // cnt}, after its proxy fence @{p1 // cnt}, first operands landed @{p2 // cnt}, last MMA committed @{p3 // cnt}")
     for key, (cnt, cyc, s0, s1, s2) in sorted(summ.items(), key=lambda t: -t[1][1]):
         print(f"   {key:28s} x{cnt:3d}  {cyc:9d} cyc  avg {cyc // cnt:7d}  ({100.0 * cyc / tot:4.1f} %)   CTA0 avg: accumulator ready @{s0 // cnt}, "
               f"epilogue done @{s1 // cnt}, barrier entered @{s2 // cnt}")
