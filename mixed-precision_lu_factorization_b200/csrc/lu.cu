@@ -14,6 +14,7 @@
 // The whole schedule is captured once into a CUDA graph per (n, options) and replayed.
 // No host<->device round trips inside the loop (the reference does one per panel, MPF.cu:146,158).
 #include "lu_internal.h"
+#include "../../include/mplu_debug.h"
 
 #include <vector>
 
@@ -1590,13 +1591,13 @@ int mplu_diag_lu128(float* dW, long long ldw, float* dLinv, float* dUinv, void* 
     CKI(panel_init());
     uint16_t* tmp16 = nullptr;
     float* sc = nullptr;
-    CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
-    CK(cudaMalloc(&sc, 4 * sizeof(float)));
+    int rc = (int)cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t));
+    if (!rc) rc = (int)cudaMalloc(&sc, 4 * sizeof(float));
     // the kernel stores triangles only
-    CK(cudaMemsetAsync(dLinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream));
-    CK(cudaMemsetAsync(dUinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream));
-    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
-                            (cudaStream_t)stream);
+    if (!rc) rc = (int)cudaMemsetAsync(dLinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream);
+    if (!rc) rc = (int)cudaMemsetAsync(dUinv, 0, 128 * 128 * sizeof(float), (cudaStream_t)stream);
+    if (!rc) rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
+                                 (cudaStream_t)stream);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(tmp16);
     cudaFree(sc);
@@ -1609,10 +1610,10 @@ int mplu_diag_lu128_timed(float* dW, long long ldw, float* dLinv, float* dUinv, 
     CKI(panel_init());
     uint16_t* tmp16 = nullptr;
     float* sc = nullptr;
-    CK(cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t)));
-    CK(cudaMalloc(&sc, 4 * sizeof(float)));
-    int rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
-                            (cudaStream_t)stream, d_clocks);
+    int rc = (int)cudaMalloc(&tmp16, 2 * 128 * 128 * sizeof(uint16_t));
+    if (!rc) rc = (int)cudaMalloc(&sc, 4 * sizeof(float));
+    if (!rc) rc = launch_diag_lu(dW, ldw, 0, tmp16, tmp16 + 128 * 128, 128, dLinv, dUinv, sc, 1, 0, 0, nullptr,
+                                 (cudaStream_t)stream, d_clocks);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(tmp16);
     cudaFree(sc);
@@ -1627,41 +1628,49 @@ int mplu_bench_gemm_chain(int variant, int M, int N, int K, int reps, int pdl, i
     if (gemm_tc_init() != 0) return MPLU_E_TMAP;
     uint16_t *A = nullptr, *B = nullptr, *H = nullptr;
     float* Cm = nullptr;
-    CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)K * N * 2));
-    CK(cudaMalloc(&H, (size_t)M * N * 2)); CK(cudaMalloc(&Cm, (size_t)M * N * 4));
-    CK(cudaMemset(A, 0, (size_t)M * K * 2)); CK(cudaMemset(B, 0, (size_t)K * N * 2));
-    CK(cudaMemset(Cm, 0, (size_t)M * N * 4));
-    uint32_t abr, abc, bbr, bbc;
-    gemm_box_shapes(variant, &abr, &abc, &bbr, &bbc);
-    CUtensorMap tA, tB;
-    if (make_tmap_16bit(&tA, A, M, K, M, abr, abc)) return MPLU_E_TMAP;
-    if (make_tmap_16bit(&tB, B, K, N, K, bbr, bbc)) return MPLU_E_TMAP;
-    GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.C = Cm; p.ldc = M; p.Cin = accumulate ? Cm : nullptr; p.ldcin = M;
-    p.H = shadow ? H : nullptr; p.ldh = M; p.h_rows = M; p.h_cols = N; p.alpha = -1.f; p.hscale = 1.f; p.pdl = pdl;
-    cudaStream_t st;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaStream_t st = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    int rc = 0;
-    for (int i = 0; i < reps && !rc; ++i) rc = launch_gemm_tc(variant, &tA, &tB, p, max_sms, st);
-    CK(cudaStreamEndCapture(st, &graph));
-    if (rc) return rc;
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaGraphLaunch(exec, st));
-    CK(cudaEventRecord(e0, st));
-    CK(cudaGraphLaunch(exec, st));
-    CK(cudaEventRecord(e1, st));
-    CK(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    *us_per_launch = 1e3f * ms / reps;
-    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaStreamDestroy(st); cudaFree(A); cudaFree(B); cudaFree(H); cudaFree(Cm);
-    return 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto body = [&]() -> int {  // every exit path goes through the clean-up below
+        CK(cudaMalloc(&A, (size_t)M * K * 2)); CK(cudaMalloc(&B, (size_t)K * N * 2));
+        CK(cudaMalloc(&H, (size_t)M * N * 2)); CK(cudaMalloc(&Cm, (size_t)M * N * 4));
+        CK(cudaMemset(A, 0, (size_t)M * K * 2)); CK(cudaMemset(B, 0, (size_t)K * N * 2));
+        CK(cudaMemset(Cm, 0, (size_t)M * N * 4));
+        uint32_t abr, abc, bbr, bbc;
+        gemm_box_shapes(variant, &abr, &abc, &bbr, &bbc);
+        CUtensorMap tA, tB;
+        if (make_tmap_16bit(&tA, A, M, K, M, abr, abc)) return MPLU_E_TMAP;
+        if (make_tmap_16bit(&tB, B, K, N, K, bbr, bbc)) return MPLU_E_TMAP;
+        GemmParams p{};
+        p.M = M; p.N = N; p.K = K; p.C = Cm; p.ldc = M; p.Cin = accumulate ? Cm : nullptr; p.ldcin = M;
+        p.H = shadow ? H : nullptr; p.ldh = M; p.h_rows = M; p.h_cols = N; p.alpha = -1.f; p.hscale = 1.f; p.pdl = pdl;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        int rc = 0;
+        for (int i = 0; i < reps && !rc; ++i) rc = launch_gemm_tc(variant, &tA, &tB, p, max_sms, st);
+        CK(cudaStreamEndCapture(st, &graph));
+        if (rc) return rc;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaGraphLaunch(exec, st));
+        CK(cudaEventRecord(e0, st));
+        CK(cudaGraphLaunch(exec, st));
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        *us_per_launch = 1e3f * ms / reps;
+        return 0;
+    };
+    const int rc = body();
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(A); cudaFree(B); cudaFree(H); cudaFree(Cm);
+    return rc;
 }
 
 // Dry run of the device factorization schedule for an n x n matrix (host logic only, no device needed): what would be
