@@ -72,7 +72,7 @@ typedef struct mplu_options {
                          (same factors bit for bit; n=32768: 35.8 vs 38.3 ms) */
     int eager;        /* MPLU_SCHED_LEFT: 1 (default) = the bulk lane spends each step's share of the remaining update work
                          ahead of need on the columns further right (balances the lanes); 0 = strictly left-looking */
-    int side_sms_left;/* MPLU_SCHED_LEFT: SMs of the chain lane (default 24; side_sms / side_sms_early are the right-looking
+    int side_sms_left;/* MPLU_SCHED_LEFT: SMs of the chain lane (default 16; side_sms / side_sms_early are the right-looking
                          schedule's) */
     int stream_c;     /* 1 (default): the tall rank-nb updates load / store their fp32 C and 16-bit shadow with the streaming
                          (evict-first) cache policy: that traffic is touched once per launch and far larger than L2 */
@@ -91,6 +91,14 @@ typedef struct mplu_options {
                          tile's first Schur update takes its addend straight from the caller's fp64 matrix (the cast is fused
                          into the GEMM epilogue's loads) and ||A||_inf is formed by the first residual pass.  An entry that
                          leaves the fp16 range under that scale is detected and the factorization redone the eager way */
+    int flow_w;       /* GETRF of a diagonal block of at most flow_w columns (128 * a power of two) runs as ONE dataflow launch
+                         (csrc/getrf_flow.cu): right-looking at 128-block granularity, two CTAs run leaf after leaf, the others
+                         pull 128x128 tile products from a priority-ordered task list and hand results over through counters
+                         in global memory -- no grid barriers, no merged inverse between two leaves.  Takes precedence over
+                         fuse_w for the widths it covers; default 2048, 0 = off.  Factors agree with the other paths to rounding level
+                         (the Schur updates are summed in rank-128 pieces) */
+    int flow_ctas;    /* CTAs (= SMs) of that launch, even, >= 4 (2 leaf CTAs + helpers), default 16 */
+    int flow_merge_ctas; /* helpers that take inverse-merge tasks before main-list tasks; -1 (default) = a quarter of them */
 } mplu_options;
 
 typedef struct mplu_stats {

@@ -30,6 +30,15 @@ int mplu_debug_fused_profile_enable(mplu_context *ctx, int on);
 int mplu_debug_fused_profile(mplu_context *ctx, int launch, long long *out, int max_records);
 int mplu_debug_fused_raw(mplu_context *ctx, int launch, long long *out, int max_slots);
 
+/* %globaltimer stamps of the `launch`-th dataflow GETRF launch (csrc/getrf_flow.cu) of the following factorizations
+ * (launch < 0: off; takes effect at the next schedule capture).  _profile, after a synchronised factorization:
+ * stamps[0 .. 2 L) = (start, end) ns of the L leaves, then four per task of the list (taken from the queue, dependencies
+ * met, result signalled, CTA); tasks_out receives the 32-byte FlowTask records (kind / step in the padding).  Returns the
+ * task count */
+int mplu_debug_flow_profile_enable(mplu_context *ctx, int launch);
+int mplu_debug_flow_profile(mplu_context *ctx, long long *stamps, int max_stamps, unsigned char *tasks_out, int max_task_bytes,
+                            int *num_leaves);
+
 /* the fp32 inverses of the unit-lower / upper factor of diagonal 128-block `blk` (column-major 128 x 128 each, device
  * or host destination), as the triangular solves use them */
 int mplu_debug_block_inverses(mplu_context *ctx, int blk, float *Linv, float *Uinv);

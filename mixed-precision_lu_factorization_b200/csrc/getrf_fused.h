@@ -63,4 +63,49 @@ int getrf_fused_init();  // per-device kernel attributes
 // grid of `num_ctas` (even, >= 2) CTAs in clusters of two, all of which must be able to be resident at the same time
 int launch_getrf_fused(const FusedMaps& maps, const FusedArgs& args, int num_ctas, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Dataflow GETRF (getrf_flow.cu): the same diagonal block factored RIGHT-looking at 128-block granularity by one
+// persistent launch WITHOUT grid barriers.  CTAs 0/1 run leaf after leaf; every other CTA is a helper that pulls 128x128
+// tile products (panel solves with a leaf's inverses, rank-128 Schur updates, inverse merges) from one priority-ordered
+// task list through an atomic queue head.  Dependencies are explicit: a task waits until up to four counters in global
+// memory have reached their targets and bumps up to three counters once its result tile is globally visible.
+struct alignas(16) FlowTask {
+    uint16_t problem;      // index into the problems; 0xFFFF = stop marker
+    uint8_t mt, nt;        // output tile of that problem
+    uint8_t kb0, kb1;      // 64-wide k-blocks [kb0, kb1) (triangular operands: the non-zero part)
+    uint16_t wait_ctr[4];  // 0xFFFF = unused
+    uint16_t wait_val[4];
+    uint16_t sig_ctr[3];   // 0xFFFF = unused
+    uint16_t pad_[2];
+};
+static_assert(sizeof(FlowTask) == 32, "FlowTask layout");
+
+struct alignas(16) FlowLeaf {
+    int k0, blk, first_in_tile, valid, T;
+    uint16_t wait_ctr, wait_val;  // the block has received all of its updates (0xFFFF: no wait)
+    uint16_t sig_ctr, pad_;       // bumped by BOTH leaf CTAs when L\U and the block inverses are visible (target 2)
+    int pad2_;
+};
+static_assert(sizeof(FlowLeaf) == 32, "FlowLeaf layout");
+
+struct FlowArgs {
+    const FlowLeaf* leaves; int num_leaves;
+    const FusedProblem* problems; int num_problems;
+    const FlowTask* tasks; int num_tasks;
+    int num_main;         // tasks [0, num_main): leaf-to-leaf chain and updates; [num_main, num_tasks): inverse merges
+    int merge_ctas;       // the last merge_ctas helper CTAs take merge tasks first, the others main tasks first
+    unsigned* counters;   // device words, zero before the launch; [0] / [1] = queue heads of the two lists
+    float* W; long long ldw;
+    void* Linv16; void* Uinv16; long long ld16;
+    float* Linv32; float* Uinv32;
+    float* inv_scales;
+    int bf16;
+    int* status;
+    long long* dbg;       // development aid: per leaf (start, end) and per task (dependencies met, signalled) in %globaltimer ns
+};
+
+int getrf_flow_init();  // per-device kernel attributes
+// grid of `num_ctas` (even, >= 4) CTAs in clusters of two, all of which must be able to be resident at the same time
+int launch_getrf_flow(const FusedMaps& maps, const FlowArgs& args, int num_ctas, cudaStream_t st);
+
 }  // namespace mplu

@@ -16,6 +16,9 @@
 #include "lu_internal.h"
 #include "../../include/mplu_debug.h"
 
+#include <algorithm>
+#include <cstring>
+#include <functional>
 #include <vector>
 
 #include <cmath>
@@ -34,6 +37,10 @@ void free_work(mplu_context* c) {
     cudaFree(c->slab);
     cudaFree(c->rowsum_part); cudaFree(c->r); cudaFree(c->partial); cudaFree(c->y);
     cudaFree(c->fprog_dev); cudaFree(c->fbar); cudaFree(c->fprof);
+    cudaFree(c->flow_dev); cudaFree(c->fctr); cudaFree(c->flow_prof);
+    c->flow_dev = nullptr; c->flow_cap = 0; c->flow_uploaded = 0; c->fctr = nullptr; c->fctr_cap = 0;
+    c->flow_prof = nullptr; c->flow_prof_cap = 0;
+    c->flow_progs.clear(); c->flow_host.clear(); c->flow_key.clear();
     c->fprof = nullptr;
     c->fprog_dev = nullptr; c->fprog_cap = 0; c->fbar = nullptr; c->fbar_cap = 0;
     c->fprogs.clear(); c->fprog_host.clear(); c->fprog_key.clear(); c->fprog_uploaded = 0;
@@ -100,6 +107,14 @@ int ensure_work(mplu_context* c, int n) {
         c->fbar_cap = (int)(np / kDiagBlock) + 16;
         CK(cudaMalloc(&c->fbar, c->fbar_cap * sizeof(unsigned)));
         CK(cudaMemset(c->fbar, 0, c->fbar_cap * sizeof(unsigned)));
+        {   // dataflow GETRF: task lists (a block of b 128-blocks has ~b^3/3 tile tasks of 32 bytes) and dependency counters
+            const size_t b = nb / kDiagBlock, tiles = np / nb + 1;
+            c->flow_cap = tiles * (32 * (b * b * b / 3 + 4 * b * b + 16) + 1024 * b) + 65536;
+            CK(cudaMalloc(&c->flow_dev, c->flow_cap));
+            c->fctr_cap = (int)(tiles * (3 * b * b + 8 * b + 16)) + 64;
+            CK(cudaMalloc(&c->fctr, (size_t)c->fctr_cap * sizeof(unsigned)));
+            CK(cudaMemset(c->fctr, 0, (size_t)c->fctr_cap * sizeof(unsigned)));
+        }
         c->cap_npad = npad;
         c->cap_nb = NB;
     }
@@ -223,6 +238,9 @@ int traced_cast(mplu_context* c, int r0, int c0, int rows, int cols, cudaStream_
 int reset_fused_barriers(mplu_context* c, cudaStream_t st) {
     c->fbar_next = 0;
     if (c->fbar) CK(cudaMemsetAsync(c->fbar, 0, (size_t)c->fbar_cap * sizeof(unsigned), st));
+    c->fctr_next = 0;
+    c->flow_launch_count = 0;
+    if (c->fctr) CK(cudaMemsetAsync(c->fctr, 0, (size_t)c->fctr_cap * sizeof(unsigned), st));
     return 0;
 }
 int traced_clear_bands(mplu_context* c, cudaStream_t st) {
@@ -289,6 +307,36 @@ int fused_map_of(const mplu_context* c, const Operand16* o) {
     return FM_T2;
 }
 
+// one product as the descriptor the persistent GETRF kernels interpret; false: a shape they cannot express
+bool to_fused_problem(const mplu_context* c, const GemmCall& g, FusedProblem* out) {
+    bool ok = true;
+    FusedProblem p{};
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.a_map = fused_map_of(c, g.A); p.a_r0 = g.a_r0; p.a_c0 = g.a_c0;
+    p.b_map = fused_map_of(c, g.B); p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
+    p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
+    p.accumulate = g.accumulate ? 1 : 0;
+    p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2; p.hscale_p = g.hscale_p;
+    p.c_r0 = p.c_c0 = -1;
+    if (g.C) {  // the fp32 result always lives in W
+        const long long off = g.C - c->W;
+        p.c_r0 = (int)(off % g.ldc); p.c_c0 = (int)(off / g.ldc);
+        if (g.ldc != c->npad) ok = false;
+    }
+    p.h_map = -1;
+    if (g.H) {  // the 16-bit copy is a whole-tile store: inside a GETRF every product shadows all of its result
+        int arr = 0, hr = 0, hc = 0;
+        if (trace_locate16(c, g.H, g.ldh, &arr, &hr, &hc) && (g.h_rows >= g.M || g.h_cols >= g.N)) {
+            p.h_map = arr - TA_WH; p.h_r0 = hr; p.h_c0 = hc;
+        } else {
+            ok = false;
+        }
+    }
+    if (g.accumulate && !g.C) ok = false;
+    *out = p;
+    return ok;
+}
+
 void rec_gemm_step(mplu_context* c, const GemmCall* calls, int count) {
     FusedStep st{};
     st.kind = FS_GEMM;
@@ -298,28 +346,7 @@ void rec_gemm_step(mplu_context* c, const GemmCall* calls, int count) {
         const GemmCall& g = calls[i];
         if (g.M <= 0 || g.N <= 0 || g.K <= 0) continue;
         FusedProblem p{};
-        p.M = g.M; p.N = g.N; p.K = g.K;
-        p.a_map = fused_map_of(c, g.A); p.a_r0 = g.a_r0; p.a_c0 = g.a_c0;
-        p.b_map = fused_map_of(c, g.B); p.b_r0 = g.b_r0; p.b_c0 = g.b_c0;
-        p.tri = c->opts.tri_skip ? g.tri : TRI_NONE;
-        p.accumulate = g.accumulate ? 1 : 0;
-        p.alpha = g.alpha; p.alpha_p1 = g.alpha_p1; p.alpha_p2 = g.alpha_p2; p.hscale_p = g.hscale_p;
-        p.c_r0 = p.c_c0 = -1;
-        if (g.C) {  // the fp32 result always lives in W
-            const long long off = g.C - c->W;
-            p.c_r0 = (int)(off % g.ldc); p.c_c0 = (int)(off / g.ldc);
-            if (g.ldc != c->npad) c->rec->unsupported = true;
-        }
-        p.h_map = -1;
-        if (g.H) {  // the 16-bit copy is a whole-tile store: inside a GETRF every product shadows all of its result
-            int arr = 0, hr = 0, hc = 0;
-            if (trace_locate16(c, g.H, g.ldh, &arr, &hr, &hc) && (g.h_rows >= g.M || g.h_cols >= g.N)) {
-                p.h_map = arr - TA_WH; p.h_r0 = hr; p.h_c0 = hc;
-            } else {
-                c->rec->unsupported = true;
-            }
-        }
-        if (g.accumulate && !g.C) c->rec->unsupported = true;
+        if (!to_fused_problem(c, g, &p)) c->rec->unsupported = true;
         c->rec->problems.push_back(p);
         tiles += (g.M / kDiagBlock) * (g.N / kDiagBlock);
         st.tile_end[st.num_problems++] = tiles;
@@ -410,6 +437,12 @@ int upload_fused_programs(mplu_context* c, cudaStream_t st) {
         CK(cudaMemcpyAsync(c->fprog_dev + c->fprog_uploaded, c->fprog_host.data() + c->fprog_uploaded, have - c->fprog_uploaded,
                            cudaMemcpyHostToDevice, st));
         c->fprog_uploaded = have;
+    }
+    const size_t fhave = c->flow_host.size();
+    if (fhave > c->flow_uploaded) {
+        CK(cudaMemcpyAsync(c->flow_dev + c->flow_uploaded, c->flow_host.data() + c->flow_uploaded, fhave - c->flow_uploaded,
+                           cudaMemcpyHostToDevice, st));
+        c->flow_uploaded = fhave;
     }
     return 0;
 }
@@ -521,7 +554,254 @@ struct Sched {
         c->kernel_launches++;
         return launch_getrf_fused(c->fmaps, a, G, ln.st);
     }
+    // ---- dataflow GETRF (getrf_flow.cu): the block as a right-looking task list with explicit dependency counters
+    bool flow(int w) const {
+        const int b = w / kDiagBlock;
+        return !c->trace && !c->rec && c->opts.flow_w > kDiagBlock && w > kDiagBlock && w <= c->opts.flow_w && w % kDiagBlock == 0 &&
+               (b & (b - 1)) == 0 && c->npad % kDiagBlock == 0 && b <= 128;
+    }
+    struct FlowBuild {
+        std::vector<FlowLeaf> leaves;
+        std::vector<FusedProblem> problems;
+        std::vector<FlowTask> tasks;
+        int num_main = 0;  // tasks [0, num_main): main list, the rest: inverse merges
+        int nctr = 2;      // counters 0 / 1 are the queue heads of the two lists
+        bool unsupported = false;
+    };
+    enum FlowKind : int { FK_PL = 0, FK_PU = 1, FK_S = 2, FK_T1 = 3, FK_T2 = 4, FK_X = 5, FK_Y = 6 };
+    // Task list of GETRF([c0, c0+w)^2) inside tile T.  Counters: LD[i] leaf i done (2 = both CTAs); LR[j][i] / UR[i][k] panel
+    // tile final; V[j][k] rank-128 updates applied to tile (j,k); per merge node: NL / NU (panel tiles of its off-diagonal
+    // block final), MT1 / MT2 (first merge products), MX / MY (merged inverse of the node complete).
+    // Two lists, each in priority order and each a topological order (a helper may hold an entry and wait: the earliest
+    // unfinished entry of a list can always run; main entries never wait for merges):
+    //   main:    A_0 B_0 | A_1 C_0 B_1 | A_2 C_1 B_2 | ...
+    //     A_i: L(i+1,i), U(i,i+1), the update of D_{i+1}: all that separates leaf i+1 from leaf i
+    //     B_i: the other panel tiles of step i, then the updates of the three tiles step i+1's A-group reads
+    //     C_i: the rest of update i, tiles of row / column i+1 first
+    //   merges:  M_0 M_1 ...   M_i: merge products whose inputs exist after step i.  The second product of a merge,
+    //     X21 = -inv(Lb) T1, waits per tile ROW for that row of inv(Lb) (per column of inv(Ub) on the U side), so after the
+    //     last leaf only one row of tiles per level is left instead of four whole levels.
+    void build_flow(int T, int c0, int w, FlowBuild& fb) const {
+        const int nblk = w / kDiagBlock, end = c0 + w;
+        auto newc = [&]() { return fb.nctr++; };
+        std::vector<int> LD(nblk), LR(nblk * nblk, -1), UR(nblk * nblk, -1), V(nblk * nblk, -1), NLc(nblk * nblk, -1), NUc(nblk * nblk, -1);
+        for (int i = 0; i < nblk; ++i) LD[i] = newc();
+        for (int i = 0; i < nblk; ++i)
+            for (int j = i + 1; j < nblk; ++j) { LR[j * nblk + i] = newc(); UR[i * nblk + j] = newc(); }
+        for (int j = 1; j < nblk; ++j)
+            for (int k = 1; k < nblk; ++k) V[j * nblk + k] = newc();
+        std::vector<std::vector<FlowTask>> A(nblk), Bp(nblk), Bs(nblk), Cs(nblk), Cm(nblk);
+        auto add_problem = [&](const GemmCall& g) {
+            FusedProblem p{};
+            if (!to_fused_problem(c, g, &p)) fb.unsupported = true;
+            fb.problems.push_back(p);
+            return (int)fb.problems.size() - 1;
+        };
+        auto mk = [&](int prob, int mt, int nt, int kind, int step) {
+            const FusedProblem& p = fb.problems[prob];
+            int k0 = 0, k1 = p.K;
+            const int mlo = mt * kDiagBlock, mhi = mlo + kDiagBlock, nlo = nt * kDiagBlock, nhi = nlo + kDiagBlock;
+            if (p.tri == TRI_A_LOWER) k1 = std::min(p.K, mhi);
+            else if (p.tri == TRI_A_UPPER) k0 = std::min(mlo, p.K - 64);
+            else if (p.tri == TRI_B_UPPER) k1 = std::min(p.K, nhi);
+            else if (p.tri == TRI_B_LOWER) k0 = std::min(nlo, p.K - 64);
+            FlowTask t{};
+            t.problem = (uint16_t)prob; t.mt = (uint8_t)mt; t.nt = (uint8_t)nt;
+            t.kb0 = (uint8_t)(k0 / 64); t.kb1 = (uint8_t)((k1 + 63) / 64);
+            for (int i = 0; i < 4; ++i) { t.wait_ctr[i] = 0xFFFF; t.wait_val[i] = 0; }
+            for (int i = 0; i < 3; ++i) t.sig_ctr[i] = 0xFFFF;
+            t.pad_[0] = (uint16_t)kind; t.pad_[1] = (uint16_t)step;
+            if (prob > 0xFFFE || mt > 255 || nt > 255 || (k1 + 63) / 64 > 255) fb.unsupported = true;
+            return t;
+        };
+        auto wait = [&](FlowTask& t, int ctr, int val) {
+            for (int i = 0; i < 4; ++i)
+                if (t.wait_ctr[i] == 0xFFFF) { t.wait_ctr[i] = (uint16_t)ctr; t.wait_val[i] = (uint16_t)val; return; }
+            fb.unsupported = true;
+        };
+        auto sig = [&](FlowTask& t, int ctr) {
+            if (ctr < 0) return;
+            for (int i = 0; i < 3; ++i)
+                if (t.sig_ctr[i] == 0xFFFF) { t.sig_ctr[i] = (uint16_t)ctr; return; }
+            fb.unsupported = true;
+        };
+        // ---- merge tree (the recursion of getrf() below, its products as tile tasks)
+        typedef std::pair<int, int> Dep;  // counter, target
+        // "inv(L) / inv(U) of this block is complete": as a whole, per block row of inv(L), per block column of inv(U)
+        struct Merged { Dep lx, ux; std::vector<Dep> lrow, ucol; };
+        struct Prev { bool have = false; Dep lx, ux; };
+        std::vector<Prev> prev(nblk + 1);  // last node of each width (in 128-blocks): its scratch slice is reused
+        std::function<Merged(int, int)> merge = [&](int n0, int nw) -> Merged {
+            if (nw <= kDiagBlock) {
+                const Dep d{LD[(n0 - c0) / kDiagBlock], 2};
+                return Merged{d, d, {d}, {d}};
+            }
+            const int h = split_width(nw), g = nw - h, n1 = n0 + h;
+            const Merged left = merge(n0, h), right = merge(n1, g);
+            const int ia0 = (n0 - c0) / kDiagBlock, ia1 = (n1 - c0) / kDiagBlock, ib1 = (n0 + nw - c0) / kDiagBlock;  // a = [ia0, ia1), b = [ia1, ib1)
+            const int NL = newc(), NU = newc(), MT1 = newc(), MT2 = newc(), MX = newc(), MY = newc();
+            for (int j = ia1; j < ib1; ++j)
+                for (int i = ia0; i < ia1; ++i) { NLc[j * nblk + i] = NL; NUc[i * nblk + j] = NU; }
+            const int gt = g / kDiagBlock, ht = h / kDiagBlock, tiles = gt * ht;
+            const long long off = ldi - nw;
+            const int p1 = add_problem(GemmCall{&c->opFh, n1, n0, &c->opLinv, n0 - T, n0, g, h, h, nullptr, 0, false,
+                                                c->Tb1 + off * ldi, ldi, g, h, 1.f, sc(SC_L_INV), ts(T) + 1, sc(SC_L), TRI_B_LOWER});
+            const int p2 = add_problem(GemmCall{&c->opUinv, n0 - T, n0, &c->opFh, n0, n1, h, g, h, nullptr, 0, false,
+                                                c->Tb2 + off * ldi, ldi, h, g, 1.f, ts(T) + 3, sc(SC_A_INV), sc(SC_L), TRI_A_UPPER});
+            const int px = add_problem(GemmCall{&c->opLinv, n1 - T, n1, &c->opT1, 0, (int)off, g, h, g, nullptr, 0, false,
+                                                c->Linv16 + (n1 - T) + (long long)n0 * ldi, ldi, g, h, -1.f, ts(T) + 1, sc(SC_L_INV), ts(T) + 0, TRI_A_LOWER});
+            const int py = add_problem(GemmCall{&c->opT2, 0, (int)off, &c->opUinv, n1 - T, n1, h, g, g, nullptr, 0, false,
+                                                c->Uinv16 + (n0 - T) + (long long)n1 * ldi, ldi, h, g, -1.f, sc(SC_L_INV), ts(T) + 3, ts(T) + 2, TRI_B_UPPER});
+            const Prev pv = prev[nw / kDiagBlock];
+            for (int nt = 0; nt < ht; ++nt)
+                for (int mt = 0; mt < gt; ++mt) {
+                    FlowTask t = mk(p1, mt, nt, FK_T1, ia1 - 1);
+                    wait(t, NL, tiles); wait(t, left.lx.first, left.lx.second);
+                    if (pv.have) wait(t, pv.lx.first, pv.lx.second);  // the previous node of this width has read the scratch slice
+                    sig(t, MT1);
+                    Cm[ia1 - 1].push_back(t);
+                    FlowTask u = mk(p2, nt, mt, FK_T2, ia1 - 1);
+                    wait(u, NU, tiles); wait(u, left.ux.first, left.ux.second);
+                    if (pv.have) wait(u, pv.ux.first, pv.ux.second);
+                    sig(u, MT2);
+                    Cm[ia1 - 1].push_back(u);
+                }
+            Merged me{Dep{MX, tiles}, Dep{MY, tiles}, left.lrow, left.ucol};
+            // rows (columns) of the b part become final one by one, in the order their leaves end
+            for (int r = 0; r < gt; ++r) {
+                const int XR = newc(), YC = newc();
+                for (int q = 0; q < ht; ++q) {
+                    FlowTask t = mk(px, r, q, FK_X, ia1 + r);
+                    wait(t, MT1, tiles); wait(t, right.lrow[r].first, right.lrow[r].second);
+                    sig(t, XR); sig(t, MX);
+                    Cm[ia1 + r].push_back(t);
+                    FlowTask u = mk(py, q, r, FK_Y, ia1 + r);
+                    wait(u, MT2, tiles); wait(u, right.ucol[r].first, right.ucol[r].second);
+                    sig(u, YC); sig(u, MY);
+                    Cm[ia1 + r].push_back(u);
+                }
+                me.lrow.push_back(Dep{XR, ht});
+                me.ucol.push_back(Dep{YC, ht});
+            }
+            prev[nw / kDiagBlock].have = true;
+            prev[nw / kDiagBlock].lx = me.lx;
+            prev[nw / kDiagBlock].ux = me.ux;
+            return me;
+        };
+        merge(c0, w);
+        // ---- leaves, panel solves, rank-128 updates
+        for (int i = 0; i < nblk; ++i) {
+            const int b = c0 + i * kDiagBlock, b1 = b + kDiagBlock;
+            FlowLeaf lf{};
+            lf.k0 = b; lf.blk = b / kDiagBlock; lf.first_in_tile = b == T; lf.T = T;
+            lf.valid = c->n - b < kDiagBlock ? c->n - b : kDiagBlock;
+            lf.wait_ctr = i > 0 ? (uint16_t)V[i * nblk + i] : 0xFFFF;
+            lf.wait_val = (uint16_t)i;
+            lf.sig_ctr = (uint16_t)LD[i];
+            fb.leaves.push_back(lf);
+            if (b1 >= end) break;
+            const int pl = add_problem(trsm_l_call(T, b, kDiagBlock, b1, end));
+            const int pu = add_problem(trsm_u_call(T, b, kDiagBlock, b1, end));
+            const int ps = add_problem(schur_call(b1, end, b1, end, b, b1, end - b1, end - b1));
+            for (int j = i + 1; j < nblk; ++j) {
+                FlowTask tl = mk(pl, j - i - 1, 0, FK_PL, i);
+                wait(tl, LD[i], 2);
+                if (i > 0) wait(tl, V[j * nblk + i], i);
+                sig(tl, LR[j * nblk + i]); sig(tl, NLc[j * nblk + i]);
+                FlowTask tu = mk(pu, 0, j - i - 1, FK_PU, i);
+                wait(tu, LD[i], 2);
+                if (i > 0) wait(tu, V[i * nblk + j], i);
+                sig(tu, UR[i * nblk + j]); sig(tu, NUc[i * nblk + j]);
+                auto& grp = j == i + 1 ? A[i] : Bp[i];
+                grp.push_back(tl); grp.push_back(tu);
+            }
+            std::vector<std::pair<int, FlowTask>> rest;
+            for (int j = i + 1; j < nblk; ++j)
+                for (int k = i + 1; k < nblk; ++k) {
+                    FlowTask t = mk(ps, j - i - 1, k - i - 1, FK_S, i);
+                    wait(t, LR[j * nblk + i], 1); wait(t, UR[i * nblk + k], 1);
+                    if (i > 0) wait(t, V[j * nblk + k], i);
+                    sig(t, V[j * nblk + k]);
+                    if (j == i + 1 && k == i + 1) A[i].push_back(t);
+                    else if (j <= i + 2 && k <= i + 2) Bs[i].push_back(t);
+                    else rest.push_back({std::min(j, k) * nblk + std::max(j, k), t});
+                }
+            std::stable_sort(rest.begin(), rest.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            for (auto& r : rest) Cs[i].push_back(r.second);
+        }
+        auto put = [&](const std::vector<FlowTask>& v) { fb.tasks.insert(fb.tasks.end(), v.begin(), v.end()); };
+        put(A[0]); put(Bp[0]); put(Bs[0]);
+        for (int i = 0; i < nblk; ++i) {
+            if (i + 1 < nblk) put(A[i + 1]);
+            put(Cs[i]);
+            if (i + 1 < nblk) { put(Bp[i + 1]); put(Bs[i + 1]); }
+        }
+        fb.num_main = (int)fb.tasks.size();
+        for (int i = 0; i < nblk; ++i) put(Cm[i]);
+        if (fb.nctr > 0xFFFE) fb.unsupported = true;
+    }
+    int getrf_flow(const Lane& ln, int T, int c0, int w) const {
+        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip,
+                                            (long long)reinterpret_cast<uintptr_t>(c->W)};
+        if (key != c->flow_key) {
+            c->flow_progs.clear(); c->flow_host.clear(); c->flow_uploaded = 0;
+            c->flow_key = key;
+        }
+        int pi = -1;
+        for (size_t i = 0; i < c->flow_progs.size(); ++i)
+            if (c->flow_progs[i].T == T && c->flow_progs[i].c0 == c0 && c->flow_progs[i].w == w) { pi = (int)i; break; }
+        if (pi < 0) {
+            FlowBuild fb;
+            build_flow(T, c0, w, fb);
+            if (fb.unsupported) return MPLU_E_ARG;
+            const size_t lb = fb.leaves.size() * sizeof(FlowLeaf), pb = fb.problems.size() * sizeof(FusedProblem),
+                         tb = fb.tasks.size() * sizeof(FlowTask);
+            const size_t off = c->flow_host.size();
+            if (off + lb + pb + tb > c->flow_cap) return MPLU_E_ARG;
+            c->flow_host.resize(off + lb + pb + tb);
+            memcpy(c->flow_host.data() + off, fb.leaves.data(), lb);
+            memcpy(c->flow_host.data() + off + lb, fb.problems.data(), pb);
+            memcpy(c->flow_host.data() + off + lb + pb, fb.tasks.data(), tb);
+            c->flow_progs.push_back({T, c0, w, off, off + lb, off + lb + pb, (int)fb.leaves.size(), (int)fb.problems.size(),
+                                     (int)fb.tasks.size(), fb.num_main, fb.nctr});
+            pi = (int)c->flow_progs.size() - 1;
+        }
+        const mplu_context::FlowProg& fp = c->flow_progs[pi];
+        if (!c->capturing) CKI(upload_fused_programs(c, ln.st));
+        if (c->fctr_next + fp.num_counters > c->fctr_cap) return MPLU_E_ARG;
+        FlowArgs a{};
+        a.leaves = reinterpret_cast<const FlowLeaf*>(c->flow_dev + fp.off_leaves); a.num_leaves = fp.num_leaves;
+        a.problems = reinterpret_cast<const FusedProblem*>(c->flow_dev + fp.off_problems); a.num_problems = fp.num_problems;
+        a.tasks = reinterpret_cast<const FlowTask*>(c->flow_dev + fp.off_tasks); a.num_tasks = fp.num_tasks;
+        a.num_main = fp.num_main;
+        a.counters = c->fctr + c->fctr_next;
+        c->fctr_next += fp.num_counters;
+        a.W = c->W; a.ldw = ld;
+        a.Linv16 = c->Linv16; a.Uinv16 = c->Uinv16; a.ld16 = ldi;
+        a.Linv32 = c->Linv32; a.Uinv32 = c->Uinv32;
+        a.inv_scales = c->inv_scales;
+        a.bf16 = c->opts.precision == MPLU_BF16;
+        a.status = c->status;
+        if (c->flow_prof && c->flow_launch_count == c->flow_prof_launch &&
+            (size_t)(2 * fp.num_leaves + 4 * fp.num_tasks) * sizeof(long long) <= c->flow_prof_cap) {
+            a.dbg = c->flow_prof;
+            c->flow_prof_prog = pi;
+        }
+        c->flow_launch_count++;
+        int G = c->opts.flow_ctas > 0 ? c->opts.flow_ctas : 16;
+        const int budget = lane_sms(c, ln);
+        if (G > budget) G = budget;
+        G -= G % 2;
+        if (G < 4) G = 4;
+        // helpers that serve the inverse merges first: about a quarter of them (measured, tools/flow_profile.py)
+        a.merge_ctas = c->opts.flow_merge_ctas >= 0 ? c->opts.flow_merge_ctas : (G - 2) / 4;
+        if (a.merge_ctas > G - 3) a.merge_ctas = G - 3;
+        c->gemm_launches++;
+        c->kernel_launches++;
+        return launch_getrf_flow(c->fmaps, a, G, ln.st);
+    }
     int getrf(const Lane& ln, int T, int c0, int w) const {
+        if (flow(w)) return getrf_flow(ln, T, c0, w);
         if (fuse(w)) return getrf_fused(ln, T, c0, w);
         if (w <= kDiagBlock) {
             const int blk = c0 / kDiagBlock;
@@ -854,7 +1134,7 @@ int enqueue_factorization_left(mplu_context* c) {
     const int nt = (npad + NB - 1) / NB;
     if (nt >= mplu_context::kMaxSteps) return MPLU_E_ARG;
     cudaStream_t st = c->stream;
-    int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 24;
+    int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 16;
     side_sms -= side_sms % 2;
     const bool two = c->opts.lookahead != 0 && side_sms >= 2 && side_sms <= c->num_sms - 16 && nt > 2;
     const Lane all{st, 0};
@@ -1093,7 +1373,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, (long long)early, (long long)lazy, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
@@ -1332,13 +1612,16 @@ void mplu_default_options(mplu_options* o) {
     o->tri_skip = 1;
     o->stream_host = 1;
     o->schedule = MPLU_SCHED_LEFT;
-    o->side_sms_left = 24;
+    o->side_sms_left = 16;
     o->eager = 1;
     o->stream_c = 1;
     o->early_scale = 0;
     o->fuse_w = 512;
     o->fuse_ctas = 8;
     o->lazy_touch = 1;
+    o->flow_w = 2048;
+    o->flow_ctas = 16;
+    o->flow_merge_ctas = -1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -1356,6 +1639,7 @@ int mplu_create(mplu_context** out, int device) {
         if (gemm_tc_init() != 0) return MPLU_E_TMAP;
         CKI(panel_init());
         CKI(getrf_fused_init());
+        CKI(getrf_flow_init());
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
@@ -1832,6 +2116,34 @@ int mplu_debug_fused_profile(mplu_context* c, int launch, long long* out, int ma
 }
 
 // the raw time-stamp slots of fused launch `launch` (layout: see getrf_fused.cu / tools/fused_profile.py)
+// Development aid: %globaltimer stamps of the `launch`-th dataflow GETRF launch of the following factorizations
+// (launch < 0: off).  Takes effect at the next schedule capture.
+int mplu_debug_flow_profile_enable(mplu_context* c, int launch) {
+    if (!c) return MPLU_E_ARG;
+    CK(cudaSetDevice(c->device));
+    if (launch >= 0 && !c->flow_prof) {
+        c->flow_prof_cap = (size_t)8 << 20;
+        CK(cudaMalloc(&c->flow_prof, c->flow_prof_cap));
+    }
+    if (c->flow_prof) CK(cudaMemset(c->flow_prof, 0, c->flow_prof_cap));
+    c->flow_prof_launch = launch;
+    return 0;
+}
+// After a synchronised factorization: stamps[0 .. 2 L) = (start, end) of the L leaves, then per task (taken from the list,
+// dependencies met, result signalled, CTA); tasks_out receives the 32-byte task records.  Returns the task count (< 0: error).
+int mplu_debug_flow_profile(mplu_context* c, long long* stamps, int max_stamps, unsigned char* tasks_out, int max_task_bytes,
+                            int* num_leaves) {
+    if (!c || !c->flow_prof || c->flow_prof_prog < 0 || c->flow_prof_prog >= (int)c->flow_progs.size()) return MPLU_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const mplu_context::FlowProg& fp = c->flow_progs[c->flow_prof_prog];
+    const int ns = 2 * fp.num_leaves + 4 * fp.num_tasks;
+    if (ns > max_stamps || fp.num_tasks * (int)sizeof(FlowTask) > max_task_bytes) return MPLU_E_ARG;
+    CK(cudaMemcpy(stamps, c->flow_prof, (size_t)ns * sizeof(long long), cudaMemcpyDeviceToHost));
+    memcpy(tasks_out, c->flow_host.data() + fp.off_tasks, (size_t)fp.num_tasks * sizeof(FlowTask));
+    *num_leaves = fp.num_leaves;
+    return fp.num_tasks;
+}
+
 int mplu_debug_fused_raw(mplu_context* c, int launch, long long* out, int max_slots) {
     if (!c || !out || !c->fprof || launch < 0 || launch >= c->fbar_cap) return 0;
     cudaSetDevice(c->device);

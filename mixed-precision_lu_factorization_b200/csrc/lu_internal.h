@@ -86,6 +86,20 @@ struct mplu_context {
     bool fprof_on = false, fprof_sub = false;
     std::vector<int> fprof_prog;  // launch index -> index into fprogs
     mplu::FusedMaps fmaps;
+    // dataflow GETRF (getrf_flow.cu): per diagonal block one blob [FlowLeaf ...][FusedProblem ...][FlowTask ...], built once
+    // per (geometry, options) and kept on the device; every launch of a factorization takes its own slice of zeroed counters
+    struct FlowProg { int T, c0, w; size_t off_leaves, off_problems, off_tasks; int num_leaves, num_problems, num_tasks, num_main, num_counters; };
+    std::vector<FlowProg> flow_progs;
+    std::vector<unsigned char> flow_host;
+    std::vector<long long> flow_key;
+    unsigned char* flow_dev = nullptr;
+    size_t flow_cap = 0, flow_uploaded = 0;
+    unsigned* fctr = nullptr;
+    int fctr_cap = 0, fctr_next = 0;
+    // development aid (mplu_debug_flow_profile): %globaltimer stamps of ONE dataflow launch of the last factorization
+    long long* flow_prof = nullptr;
+    size_t flow_prof_cap = 0;
+    int flow_prof_launch = -1, flow_launch_count = 0, flow_prof_prog = -1;
     // GEMM operand views (tensor maps) of the 16-bit arrays
     struct Operand16 {
         uint16_t* base = nullptr;

@@ -302,9 +302,11 @@ def test_fp16_overflow_falls_back_to_bf16(mplu, oracle, solver):
 
 def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
     """Grouped launches, triangular K-range skipping, lane split, CUDA graph, workspace GETRF, the left-looking schedule
-    (schedule=1), chain-lane programmatic launches and the width / grid of the fused GETRF launches only change WHEN and
-    WHERE the same products are formed: the factors are bit-identical within each of the two leaf arithmetics (fused
-    launches form the leaf's rank-32 products on the tensor cores, fuse_w = 0 with fp32 FMAs) and agree to 1e-6 between."""
+    (schedule=1), chain-lane programmatic launches and the width / grid of the persistent GETRF launches only change WHEN and
+    WHERE the same products are formed: the factors are bit-identical within each GETRF arithmetic -- the dataflow launch
+    (default; rank-128 updates, the order in which helpers take tasks must not matter), the fused step program (flow_w = 0:
+    tensor-core leaf, recursion's products) and one launch per leaf / product (fuse_w = 0: fp32 FMA leaf) -- and agree to
+    rounding level between them."""
     import torch
     n = 2304  # not a multiple of the tile size: the last tile is partial
     A = oracle.counter_matrix(n, seed=4)
@@ -317,23 +319,34 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
                   dict(stream_c=0), dict(fuse_w=0), dict(fuse_w=0, group=0), dict(fuse_w=256), dict(fuse_w=256, fuse_ctas=2),
                   dict(fuse_w=512, fuse_ctas=8, use_graph=0), dict(fuse_w=512, fuse_ctas=32, tri_skip=0), dict(lazy_touch=0),
                   dict(lazy_touch=0, fuse_w=0))
+        common = tuple(dict(flow_w=0, **kw) for kw in common) + (
+            dict(), dict(flow_ctas=4), dict(flow_ctas=24, flow_merge_ctas=0), dict(flow_merge_ctas=6, use_graph=0),
+            dict(flow_w=512, lazy_touch=0), dict(flow_w=512, lookahead=0), dict(flow_w=256), dict(flow_w=256, flow_ctas=6, group=0))
         right = tuple(dict(schedule=0, **kw) for kw in common) + (
-            dict(schedule=0, tile_ws=1), dict(schedule=0, side_sms=16, side_sms_early=8), dict(schedule=0, pdl=2))
+            dict(schedule=0, flow_w=0, tile_ws=1), dict(schedule=0, flow_w=0, side_sms=16, side_sms_early=8), dict(schedule=0, flow_w=0, pdl=2),
+            dict(schedule=0, tile_ws=1))
         left = tuple(dict(schedule=1, **kw) for kw in common) + (
-            dict(schedule=1, eager=0), dict(schedule=1, use_graph=0, side_sms_left=64), dict(schedule=1, side_sms_left=16),
-            dict(schedule=1, early_scale=1, lazy_touch=0), dict(schedule=1, early_scale=1, lazy_touch=0, use_graph=0))
+            dict(schedule=1, flow_w=0, eager=0), dict(schedule=1, flow_w=0, use_graph=0, side_sms_left=64), dict(schedule=1, flow_w=0, side_sms_left=24),
+            dict(schedule=1, flow_w=0, early_scale=1, lazy_touch=0), dict(schedule=1, flow_w=0, early_scale=1, lazy_touch=0, use_graph=0),
+            dict(schedule=1, eager=0), dict(schedule=1, side_sms_left=32, flow_ctas=32), dict(schedule=1, early_scale=1, lazy_touch=0))
         for kw in right + left:
             x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
             LU = s.factors(n)
             assert st.converged == 1
-            # two arithmetic classes: every leaf inside a fused launch (tensor-core leaf products) or none (fuse_w = 0)
-            grp = "unfused" if kw.get("fuse_w", 2048) == 0 else "fused"
+            flow_w = kw.get("flow_w", 2048)
+            if flow_w >= 512: grp = "flow"          # whole tiles as one dataflow launch
+            elif flow_w > 0: grp = "flow256"        # 256-blocks as dataflow launches, the 512-node's products as launches
+            else: grp = "unfused" if kw.get("fuse_w", 2048) == 0 else "fused"
             if grp not in ref:
                 ref[grp] = LU.clone()
             else:
                 assert torch.equal(LU, ref[grp]), kw
+        m = ref["unfused"].abs().max().item()
         d = (ref["fused"] - ref["unfused"]).abs().max().item()
-        assert 0 <= d <= 1e-5 * ref["unfused"].abs().max().item(), d
+        assert 0 <= d <= 1e-5 * m, d
+        for g in ("flow", "flow256"):  # another summation order on the same 16-bit operands
+            d = (ref[g] - ref["unfused"]).abs().max().item()
+            assert 0 <= d <= 2.0 ** -9 * m, (g, d)
     finally:
         s.close()
 
@@ -352,11 +365,11 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
     A, b = mplu.generate(n, seed=6)
     s = mplu.Solver(0)
     try:
-        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=0, precision=precision))
+        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=0, flow_w=0, precision=precision))
         LU0 = s.factors(n).clone()
         LU1 = None
         for rep in range(2):  # second pass replays the cached graph / programs
-            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=fuse_w, fuse_ctas=ctas, precision=precision))
+            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=fuse_w, fuse_ctas=ctas, flow_w=0, precision=precision))
             assert st1.converged == 1 and st1.status_bits == 0 and st1.iters <= st0.iters + 1
             assert st1.kernel_launches < st0.kernel_launches
             F = s.factors(n)
@@ -368,6 +381,44 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
         assert dU <= 1e-5 * LU0.abs().max().item(), dU  # a few dozen fp32 ulps of the diagonal: the summation order differs
         # the 16-bit inverse of a diagonal block can round the other way: one fp16 ulp of a multiplier
         assert dL <= (2.0 ** -10 if precision == 0 else 2.0 ** -7) * torch.tril(LU0, -1).abs().max().item(), dL
+        assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("n,nb,flow_w,ctas", [(2048, 512, 256, 4), (4096, 2048, 2048, 16), (4096, 1024, 1024, 8), (4096, 4096, 4096, 16),
+                                              (3000, 1024, 1024, 6), (4096, 2048, 512, 8)])
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.timeout(300)
+def test_dataflow_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, flow_w, ctas, precision):
+    """opts.flow_w: the GETRF of a diagonal block as ONE dataflow launch (csrc/getrf_flow.cu): right-looking at 128-block
+    granularity, leaf CTAs + helper CTAs that pull tile products from a priority-ordered list and hand results over through
+    counters.  Same tcgen05 products on the same 16-bit operands as the recursion, but the Schur updates are summed in
+    rank-128 pieces and the panel solves use one 128-block inverse at a time, so the factors agree to rounding level;
+    repeated runs agree bit for bit (the order in which helpers take tasks does not change any sum).  nb = 4096 exercises
+    problem descriptors read from global memory, n = 3000 the identity padding, flow_w < nb the recursion above the
+    dataflow blocks."""
+    import torch
+    A, b = mplu.generate(n, seed=6)
+    s = mplu.Solver(0)
+    try:
+        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, fuse_w=0, flow_w=0, precision=precision))
+        LU0 = s.factors(n).clone()
+        LU1 = None
+        for rep in range(3):  # later passes replay the cached graph / programs
+            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, flow_w=flow_w, flow_ctas=ctas, precision=precision))
+            assert st1.converged == 1 and st1.status_bits == 0 and st1.iters <= st0.iters + 1
+            assert st1.kernel_launches < st0.kernel_launches
+            F = s.factors(n)
+            if LU1 is None:
+                LU1 = F.clone()
+            assert torch.equal(F, LU1)
+        dU = (torch.triu(LU1) - torch.triu(LU0)).abs().max().item()
+        dL = (torch.tril(LU1, -1) - torch.tril(LU0, -1)).abs().max().item()
+        # another summation order on 16-bit operands: a few fp16 / bf16 ulps of the largest entries
+        tol = 2.0 ** -8 if precision == 0 else 2.0 ** -5
+        assert dU <= tol * LU0.abs().max().item(), dU
+        assert dL <= tol * torch.tril(LU0, -1).abs().max().item(), dL
         assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
     finally:
         s.close()

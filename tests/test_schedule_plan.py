@@ -66,5 +66,6 @@ def test_ctypes_mirrors_match_the_library(mplu):
     assert lib.mplu_sizeof_stats() == ctypes.sizeof(mplu.Stats)
     o = mplu.default_options()
     # the last fields of the struct read back the library's defaults: the mirror's field order is right to the end
-    assert (o.stream_host, o.schedule, o.side_sms_left, o.eager, o.stream_c, o.early_scale) == (1, 1, 24, 1, 1, 0)
+    assert (o.stream_host, o.schedule, o.side_sms_left, o.eager, o.stream_c, o.early_scale) == (1, 1, 16, 1, 1, 0)
     assert (o.fuse_w, o.fuse_ctas, o.lazy_touch) == (512, 8, 1)
+    assert (o.flow_w, o.flow_ctas, o.flow_merge_ctas) == (2048, 16, -1)

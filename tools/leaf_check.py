@@ -32,7 +32,7 @@ for name, A in cases.items():
     keep = {}
     for fuse in (0, 256):
         s = m.Solver(0)
-        x, st = s.gesv(dA, db, m.default_options(nb=256, fuse_w=fuse), allow_noconv=True)
+        x, st = s.gesv(dA, db, m.default_options(nb=256, fuse_w=fuse, flow_w=0), allow_noconv=True)
         LUall = s.factors(n).cpu().numpy()
         refall = lu_nopiv(A.astype(np.float64))
         eall = np.abs(LUall - refall).max() / np.abs(refall).max()
