@@ -98,6 +98,10 @@ typedef struct mplu_options {
                          fuse_w for the widths it covers; default 2048, 0 = off.  Factors agree with the other paths to rounding level
                          (the Schur updates are summed in rank-128 pieces) */
     int flow_ctas;    /* CTAs (= SMs) of that launch, even, >= 4 (2 leaf CTAs + helpers), default 16 */
+    int fp64_fallback;/* 1 (default), mplu_gesv_device / mplu_gesv_host: like LAPACK dsgesv, a solve the low-precision factors cannot
+                         deliver (16-bit overflow in fp16 and bf16, exact zero pivot, refinement stalled) is redone with an fp64
+                         LU with row pivoting (the reference's MPF algorithm on the device) + fp64 solves; reported through
+                         mplu_stats::fp64_fallback / dsgesv_iter.  0: return MPLU_E_OVERFLOW / _ZEROPIVOT / _NOCONV instead */
     int flow_merge_ctas; /* helpers that take inverse-merge tasks before main-list tasks; -1 (default) = a quarter of them */
 } mplu_options;
 
@@ -124,6 +128,10 @@ typedef struct mplu_stats {
     double trailing_bytes;  /* their algorithmic C traffic, 8*M*N bytes each (fp32 read + write) */
     int gmres_iters;        /* MPLU_REFINE_GMRES: Krylov steps summed over the refinement iterations */
     int precision_used;     /* MPLU_FP16 / MPLU_BF16: differs from the request after a bf16 fallback */
+    int fp64_fallback;      /* 1: the solution comes from the full-precision fallback (opts.fp64_fallback) */
+    int dsgesv_iter;        /* LAPACK dsgesv's ITER: >= 0 refinement iterations of a successful mixed-precision solve; < 0 the
+                               fallback ran: -2 low-precision overflow, -3 low-precision factorization unusable (zero pivot),
+                               -(max_iters + 1) refinement did not converge */
 } mplu_stats;
 
 void mplu_default_options(mplu_options *opts);

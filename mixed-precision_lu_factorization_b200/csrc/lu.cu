@@ -1622,6 +1622,7 @@ void mplu_default_options(mplu_options* o) {
     o->flow_w = 2048;
     o->flow_ctas = 16;
     o->flow_merge_ctas = -1;
+    o->fp64_fallback = 1;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -1740,7 +1741,12 @@ int mplu_gesv_device(mplu_context* c, int n, const double* dA, long long lda, co
         if (stats) memset(stats, 0, sizeof(*stats));
         rc = solve_impl(c, dA, lda, db, dx, stats);
     }
-    if (stats) stats->precision_used = c->opts.precision;
+    if (stats) {
+        stats->precision_used = c->opts.precision;
+        stats->dsgesv_iter = rc == 0 ? stats->iters : (rc == MPLU_E_OVERFLOW ? -2 : (rc == MPLU_E_NOCONV ? -(stats->iters + 1) : -3));
+    }
+    if ((rc == MPLU_E_OVERFLOW || rc == MPLU_E_ZEROPIVOT || rc == MPLU_E_NOCONV) && c->opts.fp64_fallback)
+        rc = fp64_fallback_solve(c, n, dA, lda, db, dx, rc, stats);  // dsgesv: full-precision factorization and solve
     CK(cudaEventRecord(c->ev[2], c->stream));
     CK(cudaEventSynchronize(c->ev[2]));
     if (stats) {
@@ -1787,7 +1793,12 @@ int mplu_gesv_host(mplu_context* c, int n, const double* hA, long long lda, cons
         if (rc) return rc;
         CK(cudaEventRecord(c->ev[1], st));
         rc = solve_impl(c, c->dA_stage, n, c->db_stage, c->dx_stage, stats);
-        if (stats) stats->precision_used = c->opts.precision;
+        if (stats) {
+            stats->precision_used = c->opts.precision;
+            stats->dsgesv_iter = rc == 0 ? stats->iters : (rc == MPLU_E_OVERFLOW ? -2 : (rc == MPLU_E_NOCONV ? -(stats->iters + 1) : -3));
+        }
+        if ((rc == MPLU_E_ZEROPIVOT || rc == MPLU_E_NOCONV) && c->opts.fp64_fallback)
+            rc = fp64_fallback_solve(c, n, c->dA_stage, n, c->db_stage, c->dx_stage, rc, stats);
         CK(cudaEventRecord(c->ev[2], st));
         CK(cudaEventSynchronize(c->ev[2]));
         cudaEventElapsedTime(&h2d, c->ev[3], c->ev_copy[c->copy_last]);

@@ -183,5 +183,9 @@ int getrf_resident_tile(mplu_context* c, cudaStream_t st, int w);
 int ensure_work(mplu_context* c, int n);
 // GMRES-IR: solve A d = c->r by GMRES preconditioned with the stored factors, x += d (gmres.cu)
 int gmres_correction(mplu_context* c, const double* dA, long long lda, double* dx, int* inner);
+// dsgesv-style full-precision redo of a solve the low-precision factors could not deliver (fp64_fallback.cu); `why` is the
+// MPLU_E_* code the mixed-precision path ended with
+int fp64_fallback_solve(mplu_context* c, int n, const double* dA, long long lda, const double* db, double* dx, int why,
+                        mplu_stats* stats);
 
 }  // namespace mplu_detail

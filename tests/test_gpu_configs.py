@@ -114,7 +114,7 @@ def test_config4_kappa_sweep_n16384(mplu, solver, kappa):
     del xr
     for prec in (0, 1):
         want = KAPPA_TABLE[(kappa, prec)]
-        x, st = solver.gesv(A.t(), b, mplu.default_options(precision=prec), allow_noconv=True)
+        x, st = solver.gesv(A.t(), b, mplu.default_options(precision=prec, fp64_fallback=0), allow_noconv=True)
         it, ok = want["classic"]
         assert st.converged == ok, (kappa, prec, st.as_dict())
         if ok:

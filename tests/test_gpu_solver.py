@@ -204,8 +204,47 @@ def test_zero_pivot_and_nonconvergence_are_reported(mplu, solver):
     A[0, 0] = 0.0
     A[0, 1] = A[1, 0] = 1.0  # needs pivoting: no-pivot LU hits an exact zero pivot
     with pytest.raises(mplu.MpluError) as e:
-        run(mplu, solver, A, np.ones(n))
+        run(mplu, solver, A, np.ones(n), fp64_fallback=0)
     assert e.value.code in (-6, -7, -5)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_full_precision_fallback_like_dsgesv(mplu, oracle, solver, host):
+    """LAPACK dsgesv semantics (opts.fp64_fallback = 1, the default): a solve the low-precision factors cannot deliver is
+    redone with an fp64 LU with row pivoting -- the reference's MPF algorithm (/root/reference/MPF.cu:100-241: fp16 pivot
+    discovery, fp64 elimination) on the device copy -- and fp64 solves; ITER < 0 says why (dsgesv.f).  Three causes: an
+    exact zero pivot without pivoting (-3), classic refinement stalling on an ill-conditioned matrix (-(max_iters + 1)),
+    and the healthy case for comparison (ITER = iterations >= 0, no fallback)."""
+    import torch
+    n = 512
+    rng = np.random.default_rng(3)
+    # 1. needs pivoting: zero leading pivot, otherwise well conditioned
+    A = rng.standard_normal((n, n)) + 30.0 * np.eye(n)
+    A[0, 0] = 0.0
+    A[0, 1] = A[1, 0] = 25.0
+    x_true = rng.standard_normal(n)
+    b = A @ x_true
+    def solve(A, b, **kw):
+        if host:  # pageable host buffers through mplu_gesv_host
+            hA, hb, hx = np.asfortranarray(A), np.ascontiguousarray(b), np.empty(len(b))
+            st = solver.gesv_host_ptr(len(b), hA.ctypes.data, len(b), hb.ctypes.data, hx.ctypes.data, mplu.default_options(**kw))
+            return hx, st
+        dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
+        x, st = solver.gesv(dA, torch.tensor(b, dtype=torch.float64, device="cuda"), mplu.default_options(**kw))
+        return x.cpu().numpy(), st
+    x, st = solve(A, b)
+    assert st.fp64_fallback == 1 and st.dsgesv_iter == -3 and st.converged == 1
+    assert st.backward_error <= 2 * n * EPS
+    assert np.abs(x - x_true).max() <= 1e-10 * np.abs(x_true).max()
+    # 2. kappa = 1e10: 16-bit factors are no contraction for classic refinement
+    A2, b2 = _spd(oracle, n, 1e10)
+    x2, st2 = solve(A2, b2, max_iters=8, bf16_fallback=1)
+    assert st2.fp64_fallback == 1 and st2.dsgesv_iter in (-9, -2, -3) and st2.converged == 1
+    assert st2.backward_error <= 2 * n * EPS
+    # 3. healthy matrix: no fallback, ITER counts the refinement iterations
+    A3 = oracle.counter_matrix(n, seed=2)
+    x3, st3 = solve(A3, A3.sum(axis=1))
+    assert st3.fp64_fallback == 0 and st3.dsgesv_iter == st3.iters >= 1 and st3.converged == 1
 
 
 def test_full_size_properties_n32768(mplu, solver):
@@ -271,7 +310,7 @@ def test_kappa_sweep_classic_vs_gmres_refinement(mplu, oracle, solver, kappa, pr
     import torch
     dA = cm(torch.tensor(A, dtype=torch.float64, device="cuda"))
     db = torch.tensor(b, dtype=torch.float64, device="cuda")
-    x, st = solver.gesv(dA, db, mplu.default_options(precision=prec), allow_noconv=True)
+    x, st = solver.gesv(dA, db, mplu.default_options(precision=prec, fp64_fallback=0), allow_noconv=True)
     assert bool(st.converged) == classic_ok, st.as_dict()
     xg, sg = solver.gesv(dA, db, mplu.default_options(precision=prec, refinement=mplu.REFINE_GMRES), allow_noconv=True)
     assert sg.converged == 1 and sg.gmres_iters >= sg.iters
@@ -291,7 +330,7 @@ def test_fp16_overflow_falls_back_to_bf16(mplu, oracle, solver):
     db = torch.tensor(b, dtype=torch.float64, device="cuda")
     overflowed = False
     try:
-        x, st = solver.gesv(dA, db, mplu.default_options(refinement=mplu.REFINE_GMRES, bf16_fallback=0), allow_noconv=True)
+        x, st = solver.gesv(dA, db, mplu.default_options(refinement=mplu.REFINE_GMRES, bf16_fallback=0, fp64_fallback=0), allow_noconv=True)
     except mplu.MpluError as e:
         assert e.code == -5  # MPLU_E_OVERFLOW: reported, not silent
         overflowed = True

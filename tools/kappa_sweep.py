@@ -26,7 +26,7 @@ for e in range(2, 9):
     for name, prec in (("fp16", 0), ("bf16", 1)):
         for refine in ([0, 1] if "gmres" in kv else [0]):
             o = {k: int(v) for k, v in kv.items() if k != "gmres"}
-            opts = m.default_options(precision=prec, refinement=refine, **o)
+            opts = m.default_options(precision=prec, refinement=refine, **{"fp64_fallback": 0, **o})
             x, st = s.gesv(A.t(), b, opts, allow_noconv=True)  # symmetric: the transposed view is the column-major one
             tag = name + ("_gmres" if refine else "")
             rec[tag] = dict(iters=st.iters, converged=st.converged, backward_error=st.backward_error, status=st.status_bits, gmres_iters=st.gmres_iters,
