@@ -102,6 +102,10 @@ typedef struct mplu_options {
                          deliver (16-bit overflow in fp16 and bf16, exact zero pivot, refinement stalled) is redone with an fp64
                          LU with row pivoting (the reference's MPF algorithm on the device) + fp64 solves; reported through
                          mplu_stats::fp64_fallback / dsgesv_iter.  0: return MPLU_E_OVERFLOW / _ZEROPIVOT / _NOCONV instead */
+    int edge_nb;      /* MPLU_SCHED_LEFT, device-resident input: width of the FIRST and LAST block column (multiple of 128, < nb;
+                         0 = nb, the default).  Nothing overlaps the first diagonal tile's GETRF and the last one's, so narrower
+                         tiles there shorten the two stretches in which most SMs idle -- measured neutral at n = 32768 (33.4 vs
+                         33.3 ms): the chain lane is the critical resource in EVERY step, and its 256 leaves do not get fewer */
     int flow_merge_ctas; /* helpers that take inverse-merge tasks before main-list tasks; -1 (default) = a quarter of them */
 } mplu_options;
 
@@ -182,6 +186,8 @@ int mplu_diag_lu128(float *dW, long long ldw, float *dLinv, float *dUinv, void *
  * by nb as (step, k, m0, m1, mandatory) quintuples -- update k applied to block columns [m0, m1) during step `step`.
  * Returns the number of ops; at most `max` are written to out[0 .. 5*max). */
 int mplu_debug_plan_left(int n, int nb, int eager, int *out, int max);
+int mplu_debug_tile_bounds(int n, int nb, int edge_nb, int *out, int max);
+int mplu_debug_plan_left_edge(int n, int nb, int edge_nb, int eager, int *out, int max);
 
 /* Dry run of the device factorization schedule (host logic only, no device needed): every launch with the lane it
  * runs on and the array regions it reads / writes, and every cross-lane event record / wait, serialised as ints (see

@@ -502,7 +502,8 @@ struct Sched {
     }
     int getrf_fused(const Lane& ln, int T, int c0, int w) const {
         // programs depend on the geometry, the arrays and the options that shape the products
-        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip, c->opts.group,
+        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip, c->opts.group, c->opts.nb,
+                                            c->opts.edge_nb, c->opts.fuse_w, c->opts.flow_w, c->opts.schedule,
                                             (long long)reinterpret_cast<uintptr_t>(c->W)};
         if (key != c->fprog_key) {
             c->fprogs.clear(); c->fprog_host.clear(); c->fprog_uploaded = 0;
@@ -741,8 +742,10 @@ struct Sched {
         if (fb.nctr > 0xFFFE) fb.unsupported = true;
     }
     int getrf_flow(const Lane& ln, int T, int c0, int w) const {
-        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip,
-                                            (long long)reinterpret_cast<uintptr_t>(c->W)};
+        // programs depend on the geometry (incl. the tiling: a context that switches options must not pile programs of
+        // different tilings into a buffer sized for one), the arrays and the options that shape the products
+        const std::vector<long long> key = {c->npad, c->cap_nb, ldi, c->n, c->opts.precision, c->opts.tri_skip, c->opts.nb, c->opts.edge_nb,
+                                            c->opts.flow_w, c->opts.schedule, (long long)reinterpret_cast<uintptr_t>(c->W)};
         if (key != c->flow_key) {
             c->flow_progs.clear(); c->flow_host.clear(); c->flow_uploaded = 0;
             c->flow_key = key;
@@ -1076,14 +1079,32 @@ int enqueue_factorization(mplu_context* c) {
 // first, one op per run of equally advanced columns.  An op applies update k to block columns [m0, m1).
 struct LeftOp { int step, k, m0, m1, mandatory; };
 
-std::vector<LeftOp> plan_left(int npad, int NB, bool eager) {
-    const int nt = (npad + NB - 1) / NB;
+// Block-column boundaries of the left-looking schedule: nb-wide, except that with opts.edge_nb the first and the last one are
+// narrower.  While the first diagonal tile is factored nothing else can run, and the last one has nothing left to overlap
+// with: 2 x 1.25 ms of the n = 32768 factorization with ~130 SMs idle; a 1024-wide tile there takes half as long.
+std::vector<int> tile_bounds(int npad, int NB, int edge) {
+    std::vector<int> tb{0};
+    edge = (edge / kDiagBlock) * kDiagBlock;
+    if (edge > 0 && edge < NB && npad >= 4 * NB) {
+        int pos = edge;
+        tb.push_back(pos);
+        while (npad - pos > NB + edge) { pos += NB; tb.push_back(pos); }
+        if (npad - pos > edge) tb.push_back(npad - edge);  // what is left: (rest - edge) <= NB, then the narrow last tile
+    } else {
+        for (int pos = NB; pos < npad; pos += NB) tb.push_back(pos);
+    }
+    tb.push_back(npad);
+    return tb;
+}
+
+std::vector<LeftOp> plan_left(const std::vector<int>& tb, bool eager) {
+    const int nt = (int)tb.size() - 1, npad = tb[nt];
     std::vector<LeftOp> ops;
     std::vector<int> done(nt > 0 ? nt : 1, 0);  // done[m]: block column m has received the updates k < done[m]
-    auto colb = [&](int m) { return (long long)m * NB < npad ? m * NB : npad; };
+    auto colb = [&](int m) { return tb[m < nt ? m : nt]; };
     auto cost = [&](int k, int m0, int m1) {  // flops of update k on block columns [m0, m1): panel solve + Schur update
-        const double N = colb(m1) - colb(m0);
-        return 2.0 * (npad - (k + 1) * NB) * N * NB + (double)NB * NB * N;
+        const double N = colb(m1) - colb(m0), wk = tb[k + 1] - tb[k];
+        return 2.0 * (npad - tb[k + 1]) * N * wk + wk * wk * N;
     };
     double remaining = 0.0;
     for (int m = 2; m < nt; ++m)
@@ -1131,7 +1152,9 @@ int enqueue_factorization_left(mplu_context* c) {
     const long long ld = npad;
     const int bf16 = c->opts.precision == MPLU_BF16;
     const int NB = effective_nb(c, npad);
-    const int nt = (npad + NB - 1) / NB;
+    const std::vector<int> tb = tile_bounds(npad, NB, c->opts.edge_nb);  // block column m = [tb[m], tb[m+1])
+    const int nt = (int)tb.size() - 1;
+    const int w0 = tb[1];
     if (nt >= mplu_context::kMaxSteps) return MPLU_E_ARG;
     cudaStream_t st = c->stream;
     int side_sms = c->opts.side_sms_left > 0 ? c->opts.side_sms_left : 16;
@@ -1147,20 +1170,19 @@ int enqueue_factorization_left(mplu_context* c) {
 
     if (!c->prologue_done) {  // else prologue_left() has done this part, overlapped with the first touch
         if (!c->trace) CKI(launch_scales(c->amax, c->scales, c->opts.a_exp, c->opts.l_exp, bf16, st));
-        CKI(traced_cast(c, 0, 0, npad, NB, st));
-        if (npad > NB)
-            CKI(traced_cast(c, 0, NB, NB, npad - NB, st));
+        CKI(traced_cast(c, 0, 0, npad, w0, st));
+        if (npad > w0)
+            CKI(traced_cast(c, 0, w0, w0, npad - w0, st));
         c->kernel_launches += 3;
         CKI(traced_clear_bands(c, st));
-        CKI(S.getrf(all, 0, 0, NB));
-        if (NB < npad) CKI(S.trsm_l(all, 0, 0, NB, NB, npad));
+        CKI(S.getrf(all, 0, 0, w0));
+        if (w0 < npad) CKI(S.trsm_l(all, 0, 0, w0, w0, npad));
     }
     // Two lanes: U(j, j+1), the first thing step j+1 needs, rides in the launch that ends step j on the chain lane
     // (it is independent of that step's L(j+1, j)); here for j = 0.
     bool u_done = false;
     if (two) {
-        const int e1 = (2 * NB < npad) ? 2 * NB : npad;
-        CKI(S.trsm_u(all, 0, 0, NB, NB, e1));
+        CKI(S.trsm_u(all, 0, 0, w0, tb[1], tb[2]));
         CKI(step_event(c, 1, EV_U, &ev));
         CKI(ev_record(c, ev, st));
         u_done = true;
@@ -1172,10 +1194,10 @@ int enqueue_factorization_left(mplu_context* c) {
     // GETRF / L-panel solve read it); an intermediate update only shadows tile row k+1, which the next panel solve
     // U(k+1,.) reads -- the rest would be overwritten by update k+1 anyway, and the full-shadow epilogue costs the
     // tall update a fifth of its rate (855 vs 1109 TFLOP/s at 30720 x 30720 x 2048)
-    auto big_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1, bool last) -> int {
-        return S.schur(ln, r0, npad, c0, c1, k0, k1, last ? npad - r0 : NB, last ? c1 - c0 : 0, k0 == 0);
+    auto big_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1, bool last, int next_rows) -> int {
+        return S.schur(ln, r0, npad, c0, c1, k0, k1, last ? npad - r0 : next_rows, last ? c1 - c0 : 0, k0 == 0);
     };
-    auto timed_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1) -> int {
+    auto timed_schur = [&](const Lane& ln, int r0, int c0, int c1, int k0, int k1, int next_rows) -> int {
         // every rank-nb update of the bulk lane is timed with its own event pair for the roofline figure
         const bool timed = !c->trace && c->trail_count < mplu_context::kMaxTrail;
         if (timed) {
@@ -1183,7 +1205,7 @@ int enqueue_factorization_left(mplu_context* c) {
             if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
             CKI(record_event(c, e0, ln.st));
         }
-        CKI(big_schur(ln, r0, c0, c1, k0, k1, false));
+        CKI(big_schur(ln, r0, c0, c1, k0, k1, false, next_rows));
         if (timed) {
             CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], ln.st));
             c->trail_count++;
@@ -1192,18 +1214,18 @@ int enqueue_factorization_left(mplu_context* c) {
         }
         return 0;
     };
-    auto colb = [&](int m) { return m * NB < npad ? m * NB : npad; };
+    auto colb = [&](int m) { return tb[m < nt ? m : nt]; };
     auto apply = [&](int k, int m0, int m1) -> int {
-        const int k0 = k * NB, k1 = k0 + NB, d0 = colb(m0), d1 = colb(m1);
-        CKI(S.trsm_u(bulk, k0, k0, NB, d0, d1));
-        return timed_schur(bulk, k1, d0, d1, k0, k1);
+        const int k0 = tb[k], k1 = tb[k + 1], d0 = colb(m0), d1 = colb(m1);
+        CKI(S.trsm_u(bulk, k0, k0, k1 - k0, d0, d1));
+        return timed_schur(bulk, k1, d0, d1, k0, k1, colb(k + 2) - k1);  // tile row k+1 is what the next panel solve reads
     };
-    const std::vector<LeftOp> plan = plan_left(npad, NB, c->opts.eager != 0);
+    const std::vector<LeftOp> plan = plan_left(tb, c->opts.eager != 0);
     size_t pi = 0;
     for (int j = 1; j < nt; ++j) {
-        const int c0 = j * NB, c1 = (c0 + NB < npad) ? c0 + NB : npad, w = c1 - c0;
-        const int c2 = (c1 + NB < npad) ? c1 + NB : npad;  // end of tile row j+1
-        const int kp = c0 - NB;                             // previous block column [kp, c0)
+        const int c0 = tb[j], c1 = tb[j + 1], w = c1 - c0;
+        const int c2 = colb(j + 2);  // end of tile row j+1
+        const int kp = tb[j - 1];    // previous block column [kp, c0)
         // ---- chain lane
         if (!two)  // single lane: plain left-looking, column j receives its updates k < j-1 here
             for (int k = 0; k + 2 <= j; ++k) CKI(apply(k, j, j + 1));
@@ -1213,7 +1235,7 @@ int enqueue_factorization_left(mplu_context* c) {
                 CKI(step_event(c, j, EV_COL, &ev));
                 CKI(ev_wait(c, chain.st, ev));
             }
-            CKI(S.trsm_u(chain, kp, kp, NB, c0, c1));
+            CKI(S.trsm_u(chain, kp, kp, c0 - kp, c0, c1));
             if (two) { CKI(step_event(c, j, EV_U, &ev)); CKI(ev_record(c, ev, chain.st)); }
         }
         u_done = false;
@@ -1231,7 +1253,7 @@ int enqueue_factorization_left(mplu_context* c) {
         CKI(ev_wait(c, bulk.st, ev));
         CKI(mark(c, 4000 + j, bulk.st));
         if (c1 < npad) {
-            CKI(big_schur(bulk, c1, c0, c1, kp, c0, true));
+            CKI(big_schur(bulk, c1, c0, c1, kp, c0, true, 0));
             CKI(step_event(c, j, EV_B1, &ev));
             CKI(ev_record(c, ev, bulk.st));
         }
@@ -1285,8 +1307,9 @@ int prologue_left(mplu_context* c, const double* dA, long long lda) {
     const int n = c->n, npad = c->npad;
     const long long ld = npad;
     const int bf16 = c->opts.precision == MPLU_BF16;
-    const int NB = effective_nb(c, npad);
-    const int nt = (npad + NB - 1) / NB;
+    const std::vector<int> tb = tile_bounds(npad, effective_nb(c, npad), c->opts.edge_nb);
+    const int NB = tb[1];  // the first block column
+    const int nt = (int)tb.size() - 1;
     cudaStream_t st = c->stream;
     const int s0 = c->nchunk / nt > 0 ? c->nchunk / nt : 1;  // row-sum slots of the first block column
     if (!c->ev_pro[0]) { CK(cudaEventCreateWithFlags(&c->ev_pro[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_pro[1], cudaEventDisableTiming)); }
@@ -1349,8 +1372,9 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
         const ARef href{dA, lda};
         CK(cudaMemcpyAsync(c->aref, &href, sizeof(href), cudaMemcpyHostToDevice, st));  // pageable source: staged at once
         CK(cudaMemsetAsync(c->amax, 0, sizeof(float), st));
-        CKI(launch_first_touch_cols(dA, lda, n, c->W, npad, npad, 0, NB0, c->amax, nullptr, 0, 64, st));
-        CKI(launch_first_touch_block(dA, lda, n, c->W, npad, npad, NB0, NB0, npad, c->amax, st));
+        const int w0 = tile_bounds(npad, NB0, c->opts.edge_nb)[1];  // first block column / block row
+        CKI(launch_first_touch_cols(dA, lda, n, c->W, npad, npad, 0, w0, c->amax, nullptr, 0, 64, st));
+        CKI(launch_first_touch_block(dA, lda, n, c->W, npad, npad, w0, w0, npad, c->amax, st));
     } else if (early) {
         c->gemm_launches = c->kernel_launches = 0;
         CKI(prologue_left(c, dA, lda));
@@ -1373,7 +1397,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, o.edge_nb, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
@@ -1623,6 +1647,7 @@ void mplu_default_options(mplu_options* o) {
     o->flow_ctas = 16;
     o->flow_merge_ctas = -1;
     o->fp64_fallback = 1;
+    o->edge_nb = 0;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -2034,10 +2059,32 @@ int mplu_sizeof_stats(void) { return (int)sizeof(mplu_stats); }
 
 // The left-looking schedule's bulk-lane plan for an n x n matrix tiled by nb (host logic only, no device needed):
 // (step, k, m0, m1, mandatory) quintuples into out[0 .. 5*max); returns the number of ops.
+// boundaries of the left-looking schedule's block columns for (n, nb, edge_nb); returns their count (tiles + 1)
+int mplu_debug_tile_bounds(int n, int nb, int edge, int* out, int max) {
+    if (n <= 0 || nb < kDiagBlock) return MPLU_E_ARG;
+    const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
+    nb = (nb / kDiagBlock) * kDiagBlock;
+    const std::vector<int> tb = tile_bounds(npad, nb > npad ? npad : nb, edge);
+    if (out && (int)tb.size() <= max) for (size_t i = 0; i < tb.size(); ++i) out[i] = tb[i];
+    return (int)tb.size();
+}
+// the plan for those boundaries (5 ints per op: step, k, m0, m1, mandatory)
+int mplu_debug_plan_left_edge(int n, int nb, int edge, int eager, int* out, int max) {
+    if (n <= 0 || nb < kDiagBlock) return MPLU_E_ARG;
+    const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
+    nb = (nb / kDiagBlock) * kDiagBlock;
+    const std::vector<LeftOp> ops = plan_left(tile_bounds(npad, nb > npad ? npad : nb, edge), eager != 0);
+    if (out && (int)ops.size() <= max)
+        for (size_t i = 0; i < ops.size(); ++i) {
+            out[5 * i] = ops[i].step; out[5 * i + 1] = ops[i].k; out[5 * i + 2] = ops[i].m0; out[5 * i + 3] = ops[i].m1; out[5 * i + 4] = ops[i].mandatory;
+        }
+    return (int)ops.size();
+}
+
 int mplu_debug_plan_left(int n, int nb, int eager, int* out, int max) {
     if (n <= 0 || nb < kDiagBlock || nb % kDiagBlock) return MPLU_E_ARG;
     const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
-    const std::vector<LeftOp> ops = plan_left(npad, nb > npad ? npad : nb, eager != 0);
+    const std::vector<LeftOp> ops = plan_left(tile_bounds(npad, nb > npad ? npad : nb, 0), eager != 0);
     for (size_t i = 0; i < ops.size() && (int)i < max && out; ++i) {
         out[5 * i] = ops[i].step; out[5 * i + 1] = ops[i].k; out[5 * i + 2] = ops[i].m0; out[5 * i + 3] = ops[i].m1;
         out[5 * i + 4] = ops[i].mandatory;

@@ -425,6 +425,34 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
         s.close()
 
 
+@pytest.mark.parametrize("n,nb,edge", [(8192, 1024, 512), (4096, 512, 128), (6000, 1024, 256), (16384, 2048, 1024)])
+@pytest.mark.parametrize("kw", [dict(), dict(lazy_touch=0), dict(use_graph=0, precision=1)])
+def test_narrow_edge_tiles(mplu, oracle, n, nb, edge, kw):
+    """opts.edge_nb: first and last block column of the left-looking schedule narrower than nb.  Other tile boundaries mean
+    other rank-k pieces of the same sums: factors agree with the uniform tiling to a few 16-bit ulps, the refined solution
+    is the same to fp64 accuracy, repeated runs are bit-identical."""
+    import torch
+    A, b = mplu.generate(n, seed=8)
+    s = mplu.Solver(0)
+    try:
+        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, edge_nb=0, **kw))
+        LU0 = s.factors(n).clone()
+        LU1 = None
+        for rep in range(2):
+            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, edge_nb=edge, **kw))
+            assert st1.converged == 1 and st1.status_bits == 0 and st1.iters <= st0.iters + 1
+            F = s.factors(n)
+            if LU1 is None:
+                LU1 = F.clone()
+            assert torch.equal(F, LU1)
+        tol = 2.0 ** -8 if kw.get("precision", 0) == 0 else 2.0 ** -5
+        assert (LU1 - LU0).abs().max().item() <= tol * LU0.abs().max().item()
+        assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
+        assert st1.backward_error <= 2 * n * EPS
+    finally:
+        s.close()
+
+
 @pytest.mark.parametrize("n,nb,flow_w,ctas", [(2048, 512, 256, 4), (4096, 2048, 2048, 16), (4096, 1024, 1024, 8), (4096, 4096, 4096, 16),
                                               (3000, 1024, 1024, 6), (4096, 2048, 512, 8)])
 @pytest.mark.parametrize("precision", [0, 1])

@@ -43,6 +43,47 @@ def test_left_plan_applies_every_update_once_in_order_and_in_time(mplu, n, nb, e
         assert all(mand for *_, mand in ops)                  # strictly left-looking: nothing ahead of need
 
 
+def bounds(mplu, n, nb, edge):
+    lib = mplu.load_library()
+    lib.mplu_debug_tile_bounds.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    cnt = lib.mplu_debug_tile_bounds(n, nb, edge, None, 0)
+    buf = (ctypes.c_int * cnt)()
+    assert lib.mplu_debug_tile_bounds(n, nb, edge, buf, cnt) == cnt
+    return list(buf)
+
+
+@pytest.mark.parametrize("n,nb,edge", [(32768, 2048, 1024), (32768, 2048, 512), (9000, 1152, 384), (4096, 512, 128), (8192, 1024, 512),
+                                       (2304, 512, 256), (32768, 2048, 0), (1024, 512, 256), (33000, 2048, 1024)])
+@pytest.mark.parametrize("eager", [0, 1])
+def test_left_plan_with_narrow_edge_tiles(mplu, n, nb, edge, eager):
+    """opts.edge_nb: boundaries stay multiples of 128, no block column is wider than nb, the first and last are `edge` wide
+    whenever the matrix has at least four nb-wide block columns, and the plan on those boundaries keeps its invariants."""
+    npad = -(-n // 128) * 128
+    tb = bounds(mplu, n, nb, edge)
+    assert tb[0] == 0 and tb[-1] == npad and all(b % 128 == 0 for b in tb)
+    w = [b - a for a, b in zip(tb, tb[1:])]
+    assert all(0 < x <= nb for x in w)
+    if edge and npad >= 4 * nb:
+        assert w[0] == edge and w[-1] == edge
+    else:
+        assert w[:-1] == [min(nb, npad)] * (len(w) - 1)
+    nt = len(w)
+    lib = mplu.load_library()
+    lib.mplu_debug_plan_left_edge.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    cnt = lib.mplu_debug_plan_left_edge(n, nb, edge, eager, None, 0)
+    buf = (ctypes.c_int * (5 * max(cnt, 1)))()
+    assert lib.mplu_debug_plan_left_edge(n, nb, edge, eager, buf, cnt) == cnt
+    seen = {m: [] for m in range(nt)}
+    for i in range(cnt):
+        step, k, m0, m1, mandatory = buf[5 * i:5 * i + 5]
+        assert 1 <= step <= nt - 2 and 0 <= k <= step - 1 and step + 1 <= m0 < m1 <= nt
+        for m in range(m0, m1):
+            seen[m].append((step, k))
+    for m in range(nt):
+        assert [k for _, k in seen[m]] == list(range(max(m - 1, 0))), m
+        assert all(step <= m - 1 for step, _ in seen[m])
+
+
 def test_eager_plan_balances_the_steps(mplu):
     """n=32768, nb=2048: no step carries more than ~1.5x the average update work (plain left-looking: the last step
     carries 14 updates, the first one)."""

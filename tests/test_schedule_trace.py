@@ -84,6 +84,19 @@ def test_schedule_is_race_free(mplu, n, nb, kw):
     assert leaves == list(range(0, npad, 128))
 
 
+@pytest.mark.parametrize("n,nb,edge", [(32768, 2048, 1024), (9000, 1152, 384), (4096, 512, 128), (8192, 1024, 512), (2304, 512, 256)])
+@pytest.mark.parametrize("kw", [dict(), dict(eager=0), dict(group=0)])
+def test_schedule_with_narrow_edge_tiles_is_race_free(mplu, n, nb, edge, kw):
+    """opts.edge_nb: the first and last block column narrower than nb (non-uniform boundaries through the whole left-looking
+    schedule): same vector-clock check, and every 128-leaf still factored exactly once."""
+    ops = trace(mplu, n, nb, schedule=1, edge_nb=edge, **kw)
+    launches, ordered = check(merge_groups(ops))
+    npad = -(-n // 128) * 128
+    assert launches > 0 and ordered > 0
+    leaves = sorted(r[0][1] for k, _, _, _, r in ops if k == 1)
+    assert leaves == list(range(0, npad, 128))
+
+
 def merge_groups(ops):
     """Launches that carry several problems (same group id) are ONE launch: merge their regions into one op."""
     out = []
