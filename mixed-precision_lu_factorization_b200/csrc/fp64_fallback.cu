@@ -80,8 +80,7 @@ __global__ void axpy_kernel(double* x, const double* d, int n) {
 // x <- U^-1 L^-1 P x with the fp64 factors
 int lu_solve_fp64(const double* LU, int n, const int* ipiv, const double* rhs, double* x, double* tmp, cudaStream_t st) {
     if ((size_t)n * sizeof(int) > 200 * 1024) return MPLU_E_ARG;  // the index vector must fit shared memory (n <= 51200)
-    static bool attr = false;
-    if (!attr) { CK(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    CK(cudaFuncSetAttribute(permute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  // per device: not cached
     permute_kernel<<<1, 1024, (size_t)n * sizeof(int), st>>>(rhs, tmp, ipiv, n);
     CK(cudaMemcpyAsync(x, tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     for (int k0 = 0; k0 < n; k0 += FB) {

@@ -522,8 +522,8 @@ cudaError_t mpf_device(double* d_A, int N, int r, int* d_ipiv) {
     fp16* d_mirror = nullptr;
     int *d_ipiv_panel = nullptr, *d_pos2phys = nullptr;
     unsigned long long* d_keys = nullptr;
-    static std::once_flag once;
-    std::call_once(once, []() { cudaFuncSetAttribute(dmma_rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM); });
+    // per device, and cheap: set on every call rather than cached per process
+    cudaFuncSetAttribute(dmma_rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
     const int threads = 256;
     const bool fast = r <= HP_COLS;
     const int max_hp = mplu_coop_blocks_limit((const void*)hpivot_kernel, HP_THREADS);
