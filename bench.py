@@ -277,6 +277,26 @@ def run_distributed(args, m, pk, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     fwd_err = float((xs[0] - 1).abs().max().item())
 
+    extra = dict(per_gpu_tflops=flops(n) / (ms_max * 1e-3) / 1e12 / world)
+    if args.extra_n > 0:
+        # the same curve on a system that also fits ONE GPU (bench.py --gpus 1 reports it under the same key)
+        n2 = args.extra_n
+        As2, bs2 = ds.generate(n2, nb, seed=1)
+        best = None
+        for i in range(3):
+            xs2, st2 = ds.gesv(n2, nb, As2, bs2, opts)
+            tt = torch.tensor([st2.total_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if i and (best is None or float(tt.item()) < best[0]):
+                best = (float(tt.item()), st2)
+        extra["same_system"] = dict(n=n2, n_gpus=world, value=flops(n2) / (best[0] * 1e-3) / 1e12, unit="TFLOP/s", ms=best[0],
+                                    ir_iters=best[1].iters, backward_error=best[1].backward_error,
+                                    max_abs_err=float((xs2[0] - 1).abs().max().item()),
+                                    what="ONE n x n system that fits a single GPU, 2D block-cyclic on these N GPUs")
+        del As2, bs2, xs2
+        torch.cuda.empty_cache()
+        xs, st = ds.gesv(n, nb, As, bs, opts)  # back to the headline system (workspace sized for it again)
+
     e2e = None
     if not args.no_e2e:
         try:
@@ -321,7 +341,7 @@ def run_distributed(args, m, pk, rank, world, local):
                                   avg_launch_ms=(tr_ms / tr_n) if tr_n else None,
                                   share_of_step=(tr_ms / args.steps / ms_max) if ms_max > 0 else None,
                                   traffic=(measured_traffic() or {}).get("bytes_per_launch"), traffic_detail=measured_traffic()),
-                    headline_frac_of_peak=value / world / pk["tc_sustained"])
+                    headline_frac_of_peak=value / world / pk["tc_sustained"], extra=extra)
         print(json.dumps(line), flush=True)
     ds.close()
     dist.destroy_process_group()
@@ -342,6 +362,7 @@ def main():
     ap.add_argument("--dropin-n", type=int, default=16384, help="size of the mpf_dropin leg: the repo's drop-in MPF() (reference semantics: fp16 pivot search + fp64 factors), whole call from host buffers; 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra-n", type=int, default=65536, help="second workload reported under `extra`: ONE system of this order, which fits a single GPU, solved on the same N GPUs -- the 1 -> 8 curve read on one workload (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "mplu" else args.warmup
@@ -436,6 +457,26 @@ def main():
                    max_abs_err=float((hx - 1).abs().max().item()))
         del hA
 
+    extra = None
+    if args.extra_n > 0 and world == 1:
+        # the like-for-like single-GPU point of the multi-GPU curve (bench.py --gpus N reports the same system on N GPUs)
+        n2 = args.extra_n
+        del A, b, x
+        torch.cuda.empty_cache()
+        A2, b2 = m.generate(n2, seed=1)
+        x2 = torch.empty(n2, dtype=torch.float64, device="cuda")
+        best = None
+        for i in range(3):  # first call: allocation + schedule capture
+            st2 = solver.gesv_ptr(n2, A2.data_ptr(), n2, b2.data_ptr(), x2.data_ptr(), opts)
+            if i and (best is None or st2.total_ms < best.total_ms):
+                best = st2
+        extra = dict(per_gpu_tflops=world * flops(n) / (ms_max * 1e-3) / 1e12 / world,
+                     same_system=dict(n=n2, n_gpus=1, value=flops(n2) / (best.total_ms * 1e-3) / 1e12, unit="TFLOP/s", ms=best.total_ms,
+                                      ir_iters=best.iters, backward_error=best.backward_error,
+                                      max_abs_err=float((x2 - 1).abs().max().item()),
+                                      what="ONE n x n system that fits a single GPU; `bench.py --gpus N` solves the same system block-cyclic on N GPUs"))
+        del A2, b2, x2
+
     if rank == 0:
         num_sms = torch.cuda.get_device_properties(local).multi_processor_count
         left = int(opts.schedule) == 1
@@ -469,6 +510,8 @@ def main():
                                   algorithmic_c_bytes_per_s=(tr_by / (tr_ms * 1e-3) / 1e9) if tr_ms > 0 else None,
                                   traffic=(measured_traffic() or {}).get("bytes_per_launch"), traffic_detail=measured_traffic()),
                     headline_frac_of_peak=value / world / pk["tc_sustained"])
+        if extra:
+            line["extra"] = extra
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = dict(cpu_lapack_baseline(min(n, args.cpu_n)), kind="port")
         if args.dropin_n > 0:

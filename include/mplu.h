@@ -106,6 +106,9 @@ typedef struct mplu_options {
                          0 = nb, the default).  Nothing overlaps the first diagonal tile's GETRF and the last one's, so narrower
                          tiles there shorten the two stretches in which most SMs idle -- measured neutral at n = 32768 (33.4 vs
                          33.3 ms): the chain lane is the critical resource in EVERY step, and its 256 leaves do not get fewer */
+    int pair_ts;      /* MPLU_SCHED_LEFT, two lanes: 1 = the bulk lane's small panel solves U(k, cols) share a grouped launch with the
+                         previous op's tall update when their column ranges are disjoint (fills that launch's tail instead of a
+                         one-wave launch of their own); same products, same factors */
     int flow_merge_ctas; /* helpers that take inverse-merge tasks before main-list tasks; -1 (default) = a quarter of them */
 } mplu_options;
 

@@ -1215,10 +1215,56 @@ int enqueue_factorization_left(mplu_context* c) {
         return 0;
     };
     auto colb = [&](int m) { return tb[m < nt ? m : nt]; };
+    // Bulk lane, opts.pair_ts: the panel solve U(k, cols) of an op is a one-wave launch with a triangular operand (K per
+    // tile uneven: ~35 % of the lane's rate) -- it rides in the launch of the PREVIOUS op's tall update when their column
+    // ranges are disjoint (then the two products touch disjoint data), filling that launch's tail instead of standing
+    // alone.  `pend` = an update that has been formed but not launched yet; events that must follow it wait in `pend_ev`.
+    struct Pending { bool have = false; GemmCall g{}; int c0 = 0, c1 = 0; bool timed = false; double flops = 0, bytes = 0; } pend;
+    std::vector<cudaEvent_t> pend_ev;
+    const bool pair_ts = two && c->opts.pair_ts != 0 && c->opts.group != 0;
+    // launch the pending update, optionally together with the independent panel solve `t`
+    auto launch_pending = [&](const GemmCall* t, double t_flops) -> int {
+        if (!pend.have) return t ? run_gemm(c, bulk, *t) : 0;
+        const bool timed = pend.timed && !c->trace && c->trail_count < mplu_context::kMaxTrail;
+        if (timed) {
+            cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
+            if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
+            CKI(record_event(c, e0, bulk.st));
+        }
+        if (t) { const GemmCall both[2] = {pend.g, *t}; CKI(run_gemm_group(c, bulk, both, 2)); }
+        else CKI(run_gemm(c, bulk, pend.g));
+        if (timed) {
+            CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], bulk.st));
+            c->trail_count++;
+            c->trail_flops += pend.flops + (t ? t_flops : 0.0);
+            c->trail_bytes += pend.bytes;
+        }
+        pend.have = false;
+        for (cudaEvent_t e : pend_ev) CKI(ev_record(c, e, bulk.st));
+        pend_ev.clear();
+        return 0;
+    };
+    auto record_after_pending = [&](cudaEvent_t e) -> int {
+        if (pend.have) { pend_ev.push_back(e); return 0; }
+        return ev_record(c, e, bulk.st);
+    };
     auto apply = [&](int k, int m0, int m1) -> int {
         const int k0 = tb[k], k1 = tb[k + 1], d0 = colb(m0), d1 = colb(m1);
-        CKI(S.trsm_u(bulk, k0, k0, k1 - k0, d0, d1));
-        return timed_schur(bulk, k1, d0, d1, k0, k1, colb(k + 2) - k1);  // tile row k+1 is what the next panel solve reads
+        const int next_rows = colb(k + 2) - k1;  // tile row k+1 is what the next panel solve reads
+        if (!pair_ts) {
+            CKI(S.trsm_u(bulk, k0, k0, k1 - k0, d0, d1));
+            return timed_schur(bulk, k1, d0, d1, k0, k1, next_rows);
+        }
+        const GemmCall t = S.trsm_u_call(k0, k0, k1 - k0, d0, d1);
+        const bool indep = pend.have && (d1 <= pend.c0 || d0 >= pend.c1);
+        if (indep) CKI(launch_pending(&t, (double)(k1 - k0) * (k1 - k0) * (d1 - d0)));
+        else { CKI(launch_pending(nullptr, 0.0)); CKI(run_gemm(c, bulk, t)); }
+        pend.have = true;
+        pend.g = S.schur_call(k1, npad, d0, d1, k0, k1, next_rows, 0, k0 == 0);
+        pend.c0 = d0; pend.c1 = d1; pend.timed = true;
+        pend.flops = 2.0 * (npad - k1) * (double)(d1 - d0) * (k1 - k0);
+        pend.bytes = 8.0 * (npad - k1) * (double)(d1 - d0);
+        return 0;
     };
     const std::vector<LeftOp> plan = plan_left(tb, c->opts.eager != 0);
     size_t pi = 0;
@@ -1253,9 +1299,15 @@ int enqueue_factorization_left(mplu_context* c) {
         CKI(ev_wait(c, bulk.st, ev));
         CKI(mark(c, 4000 + j, bulk.st));
         if (c1 < npad) {
-            CKI(big_schur(bulk, c1, c0, c1, kp, c0, true, 0));
+            if (pair_ts) {  // column j's final update below its diagonal tile: may share its launch with the next op's panel solve
+                pend.have = true;
+                pend.g = S.schur_call(c1, npad, c0, c1, kp, c0, npad - c1, c1 - c0, kp == 0);
+                pend.c0 = c0; pend.c1 = c1; pend.timed = false;
+            } else {
+                CKI(big_schur(bulk, c1, c0, c1, kp, c0, true, 0));
+            }
             CKI(step_event(c, j, EV_B1, &ev));
-            CKI(ev_record(c, ev, bulk.st));
+            CKI(record_after_pending(ev));
         }
         CKI(mark(c, 5000 + j, bulk.st));
         if (j + 1 < nt) {
@@ -1264,9 +1316,10 @@ int enqueue_factorization_left(mplu_context* c) {
             for (; pi < plan.size() && plan[pi].step == j && plan[pi].mandatory; ++pi)
                 CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
             CKI(step_event(c, j + 1, EV_COL, &ev));
-            CKI(ev_record(c, ev, bulk.st));
+            CKI(record_after_pending(ev));
             for (; pi < plan.size() && plan[pi].step == j; ++pi) CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
         }
+        CKI(launch_pending(nullptr, 0.0));  // nothing stays pending across the wait for this step's GETRF
         CKI(mark(c, 6000 + j, bulk.st));
         if (c2 < npad) {
             CKI(step_event(c, j, EV_G, &ev));
@@ -1397,7 +1450,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, o.edge_nb, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, o.edge_nb, o.pair_ts, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
@@ -1648,6 +1701,7 @@ void mplu_default_options(mplu_options* o) {
     o->flow_merge_ctas = -1;
     o->fp64_fallback = 1;
     o->edge_nb = 0;
+    o->pair_ts = 0;
 }
 
 int mplu_create(mplu_context** out, int device) {

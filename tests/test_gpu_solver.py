@@ -367,7 +367,9 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
         left = tuple(dict(schedule=1, **kw) for kw in common) + (
             dict(schedule=1, flow_w=0, eager=0), dict(schedule=1, flow_w=0, use_graph=0, side_sms_left=64), dict(schedule=1, flow_w=0, side_sms_left=24),
             dict(schedule=1, flow_w=0, early_scale=1, lazy_touch=0), dict(schedule=1, flow_w=0, early_scale=1, lazy_touch=0, use_graph=0),
-            dict(schedule=1, eager=0), dict(schedule=1, side_sms_left=32, flow_ctas=32), dict(schedule=1, early_scale=1, lazy_touch=0))
+            dict(schedule=1, eager=0), dict(schedule=1, side_sms_left=32, flow_ctas=32), dict(schedule=1, early_scale=1, lazy_touch=0),
+            dict(schedule=1, pair_ts=1), dict(schedule=1, pair_ts=1, eager=0, use_graph=0), dict(schedule=1, pair_ts=1, flow_w=0),
+            dict(schedule=1, pair_ts=1, flow_w=0, fuse_w=0, lazy_touch=0))
         for kw in right + left:
             x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
             LU = s.factors(n)
