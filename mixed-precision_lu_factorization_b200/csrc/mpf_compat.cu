@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,7 +72,7 @@ __global__ void laswp_kernel(double* A, long long lda, int ncols, int k, int col
 
 // U12 = L11^-1 * A12, L11 unit lower pc x pc at A[k,k], A12 = pc x ncols at A[k,k+pc]  (cublasDtrsm, MPF.cu:215-225)
 // one thread per column of A12; L11 staged in shared memory (pc <= 64) else read through L1.
-__global__ void trsm_unit_lower_kernel(double* A, long long lda, int k, int pc, int ncols) {
+__global__ void trsm_unit_lower_kernel(double* A, long long lda, int k, int pc, int col0, int ncols) {  // columns [col0, col0 + ncols)
     extern __shared__ double sL[];  // pc*pc or nothing
     const bool staged = pc <= 64;
     if (staged) {
@@ -80,7 +81,7 @@ __global__ void trsm_unit_lower_kernel(double* A, long long lda, int k, int pc, 
     }
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncols) return;
-    double* x = A + (long long)(k + pc + c) * lda + k;
+    double* x = A + (long long)(col0 + c) * lda + k;
     for (int i = 1; i < pc; ++i) {
         double s = x[i];
         for (int t = 0; t < i; ++t) {
@@ -358,21 +359,22 @@ constexpr int DM_SMEM = (DM_KC * DM_LDA + DM_KC * DM_LDB) * (int)sizeof(double);
 // a block's phases (addend loads, products, stores) are serial, so the overlap has to come from independent blocks:
 // 64 x 64 tiles / 128 threads / 4 blocks per SM (MPLU_DM_BM=128: 128 x 64 / 256 / 2, measured slower)
 __global__ void __launch_bounds__(DM_THREADS, 512 / DM_THREADS)
-dmma_rank_update_kernel(double* A, long long lda, int k, int pc, int nt) {
+dmma_rank_update_kernel(double* A, long long lda, int row0, int col0, int kk_first, int pc, int mrows, int ncols) {
+    // C = A[row0 .. row0+mrows, col0 .. col0+ncols) -= A[row0.., kk_first .. kk_first+pc) * A[kk_first .. kk_first+pc, col0..)
     extern __shared__ double dm_smem[];
     double* As = dm_smem;                  // As[kk][m]
     double* Bs = dm_smem + DM_KC * DM_LDA;  // Bs[kk][n]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp % (DM_BM / 32), wn = warp / (DM_BM / 32);
     const int r0 = blockIdx.x * DM_BM, c0 = blockIdx.y * DM_BN;
-    const double* L21 = A + (long long)k * lda + (k + pc);
-    const double* U12 = A + (long long)(k + pc) * lda + k;
-    double* C = A + (long long)(k + pc) * lda + (k + pc);
+    const double* L21 = A + (long long)kk_first * lda + row0;
+    const double* U12 = A + (long long)col0 * lda + kk_first;
+    double* C = A + (long long)col0 * lda + row0;
     double acc[4][4][2];
     // this thread's 4 x 8 addend elements: rows rb + 8 mf, columns cb + 8 nf + e
     const int rb = r0 + wm * 32 + g, cb = c0 + wn * 32 + 2 * t;
     double* Ct = C + rb + (long long)cb * lda;
-    const bool interior = r0 + DM_BM <= nt && c0 + DM_BN <= nt;
+    const bool interior = r0 + DM_BM <= mrows && c0 + DM_BN <= ncols;
     if (interior) {
 #pragma unroll
         for (int nf = 0; nf < 4; ++nf)
@@ -387,7 +389,7 @@ dmma_rank_update_kernel(double* A, long long lda, int k, int pc, int nt) {
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mf = 0; mf < 4; ++mf)
-                    acc[mf][nf][e] = (rb + mf * 8 < nt && cb + nf * 8 + e < nt) ? Ct[mf * 8 + (long long)(nf * 8 + e) * lda] : 0.0;
+                    acc[mf][nf][e] = (rb + mf * 8 < mrows && cb + nf * 8 + e < ncols) ? Ct[mf * 8 + (long long)(nf * 8 + e) * lda] : 0.0;
     }
     for (int kk0 = 0; kk0 < pc; kk0 += DM_KC) {
         const int kn = min(DM_KC, pc - kk0);
@@ -395,12 +397,12 @@ dmma_rank_update_kernel(double* A, long long lda, int k, int pc, int nt) {
 #pragma unroll
         for (int i = 0; i < DM_KC * DM_BM / DM_THREADS; ++i) {
             const int e = tid + i * DM_THREADS, m = e % DM_BM, kk = e / DM_BM;
-            As[kk * DM_LDA + m] = (kk < kn && r0 + m < nt) ? -L21[(r0 + m) + (long long)(kk0 + kk) * lda] : 0.0;
+            As[kk * DM_LDA + m] = (kk < kn && r0 + m < mrows) ? -L21[(r0 + m) + (long long)(kk0 + kk) * lda] : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < DM_KC * DM_BN / DM_THREADS; ++i) {
             const int e = tid + i * DM_THREADS, kk = e & (DM_KC - 1), n = e >> 5;
-            Bs[kk * DM_LDB + n] = (kk < kn && c0 + n < nt) ? U12[(kk0 + kk) + (long long)(c0 + n) * lda] : 0.0;
+            Bs[kk * DM_LDB + n] = (kk < kn && c0 + n < ncols) ? U12[(kk0 + kk) + (long long)(c0 + n) * lda] : 0.0;
         }
         __syncthreads();
 #pragma unroll 2
@@ -433,7 +435,7 @@ dmma_rank_update_kernel(double* A, long long lda, int k, int pc, int nt) {
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mf = 0; mf < 4; ++mf)
-                    if (rb + mf * 8 < nt && cb + nf * 8 + e < nt) Ct[mf * 8 + (long long)(nf * 8 + e) * lda] = acc[mf][nf][e];
+                    if (rb + mf * 8 < mrows && cb + nf * 8 + e < ncols) Ct[mf * 8 + (long long)(nf * 8 + e) * lda] = acc[mf][nf][e];
     }
 }
 
@@ -526,6 +528,13 @@ cudaError_t mpf_device(double* d_A, int N, int r, int* d_ipiv) {
     cudaFuncSetAttribute(dmma_rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
     const int threads = 256;
     const bool fast = r <= HP_COLS;
+    // super-panel width of the delayed updates: the largest multiple of r up to 256 (MPLU_MPF_SP=0: none)
+    int sp = r;
+    {
+        const char* env = getenv("MPLU_MPF_SP");
+        const int want = env ? atoi(env) : 256;
+        if (want > r) sp = (want / r) * r;
+    }
     const int max_hp = mplu_coop_blocks_limit((const void*)hpivot_kernel, HP_THREADS);
     bool cluster_ok = getenv("MPLU_MPF_NO_CLUSTER") == nullptr &&
                       cudaFuncSetAttribute(hpivot_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
@@ -595,9 +604,37 @@ cudaError_t mpf_device(double* d_A, int N, int r, int* d_ipiv) {
             const int nt = N - k - pc;
             if (nt > 0) {
                 const size_t sh = pc <= 64 ? (size_t)pc * pc * sizeof(double) : 0;
-                trsm_unit_lower_kernel<<<(nt + 127) / 128, 128, sh>>>(d_A, N, k, pc, nt);
-                dim3 grid((nt + DM_BM - 1) / DM_BM, (nt + DM_BN - 1) / DM_BN);
-                dmma_rank_update_kernel<<<grid, DM_THREADS, DM_SMEM>>>(d_A, N, k, pc, nt);
+                auto update = [&](int row0, int col0, int kfirst, int kw, int mrows, int ncols) {
+                    if (mrows <= 0 || ncols <= 0) return;
+                    dim3 grid((mrows + DM_BM - 1) / DM_BM, (ncols + DM_BN - 1) / DM_BN);
+                    dmma_rank_update_kernel<<<grid, DM_THREADS, DM_SMEM>>>(d_A, N, row0, col0, kfirst, kw, mrows, ncols);
+                };
+                if (sp <= r) {  // the reference's order: U12 and the whole trailing block after every panel
+                    trsm_unit_lower_kernel<<<(nt + 127) / 128, 128, sh>>>(d_A, N, k, pc, k + pc, nt);
+                    update(k + pc, k + pc, k, pc, nt, nt);
+                } else {
+                    // Super-panel [K0, K1) (classical delayed update): after a panel only the columns left of K1 are
+                    // brought up to date (U rows + all rows below: what the next panels' pivot searches read).  The columns
+                    // right of K1 are touched by the row interchanges only, until the super-panel's last panel: then, panel
+                    // by panel, their U rows are solved and the rows above K1 updated (now that every interchange of the
+                    // super-panel has been applied to them), and the block below / right of the super-panel receives ONE
+                    // rank-(K1 - K0) update.  Same interchanges and panel arithmetic as the reference; the big block's 8
+                    // rank-32 sums become one rank-256 sum: HBM traffic of the updates / 8, the kernel turns compute-bound.
+                    const int K0 = (k / sp) * sp, K1 = std::min(K0 + sp, N), e = k + pc;
+                    if (K1 > e) {
+                        trsm_unit_lower_kernel<<<(K1 - e + 127) / 128, 128, sh>>>(d_A, N, k, pc, e, K1 - e);
+                        update(e, e, k, pc, N - e, K1 - e);
+                    }
+                    if (e >= K1 && N > K1) {
+                        for (int kk = K0; kk < K1; kk += r) {
+                            const int pw = std::min(r, K1 - kk), ee = kk + pw;
+                            const size_t shh = pw <= 64 ? (size_t)pw * pw * sizeof(double) : 0;
+                            trsm_unit_lower_kernel<<<(N - K1 + 127) / 128, 128, shh>>>(d_A, N, kk, pw, K1, N - K1);
+                            update(ee, K1, kk, pw, K1 - ee, N - K1);
+                        }
+                        update(K1, K1, K0, K1 - K0, N - K1, N - K1);
+                    }
+                }
             }
         }
     }
@@ -625,11 +662,22 @@ int mpf_impl(double* h_A, int N, int r, int* IPIV) {
 #define MPF_CK(x) do { e = (x); if (e != cudaSuccess) goto fail; } while (0)
     MPF_CK(cudaMalloc(&d_A, nn * sizeof(double)));
     MPF_CK(cudaMalloc(&d_ipiv, (size_t)N * sizeof(int)));
-    MPF_CK(staged_copy(d_A, h_A, nn * sizeof(double), true));
-    MPF_CK(cudaMemcpy(d_ipiv, IPIV, (size_t)N * sizeof(int), cudaMemcpyHostToDevice));  // untouched entries survive
-    MPF_CK(mpf_device(d_A, N, r, d_ipiv));
-    MPF_CK(staged_copy(h_A, d_A, nn * sizeof(double), false));
-    MPF_CK(cudaMemcpy(IPIV, d_ipiv, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+    {
+        const bool timing = getenv("MPLU_MPF_TIMING") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
+        MPF_CK(staged_copy(d_A, h_A, nn * sizeof(double), true));
+        MPF_CK(cudaMemcpy(d_ipiv, IPIV, (size_t)N * sizeof(int), cudaMemcpyHostToDevice));  // untouched entries survive
+        const auto t1 = std::chrono::steady_clock::now();
+        MPF_CK(mpf_device(d_A, N, r, d_ipiv));
+        const auto t2 = std::chrono::steady_clock::now();
+        MPF_CK(staged_copy(h_A, d_A, nn * sizeof(double), false));
+        MPF_CK(cudaMemcpy(IPIV, d_ipiv, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+        const auto t3 = std::chrono::steady_clock::now();
+        if (timing) {
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "MPF n=%d r=%d: h2d %.1f ms, device %.1f ms, d2h %.1f ms\n", N, r, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+        }
+    }
     cudaFree(d_A); cudaFree(d_ipiv);
     return 0;
 fail:
