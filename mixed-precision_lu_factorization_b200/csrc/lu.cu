@@ -804,7 +804,12 @@ struct Sched {
         return launch_getrf_flow(c->fmaps, a, G, ln.st);
     }
     int getrf(const Lane& ln, int T, int c0, int w) const {
-        if (flow(w)) return getrf_flow(ln, T, c0, w);
+        if (flow(w)) {
+            // MPLU_E_ARG = "does not fit the task-list / counter buffers" (returned before anything is launched): the
+            // block is then factored by the step program or the recursion below instead of failing the solve
+            const int rc = getrf_flow(ln, T, c0, w);
+            if (rc != MPLU_E_ARG) return rc;
+        }
         if (fuse(w)) return getrf_fused(ln, T, c0, w);
         if (w <= kDiagBlock) {
             const int blk = c0 / kDiagBlock;
