@@ -8,6 +8,8 @@
 // Warp roles (320 threads): warps 0-7 epilogue (TMEM lanes 32*(w%4).., column half w/4), warp 8 TMA producer,
 // warp 9 TMEM allocator + MMA issuer.  Persistent: each CTA (or CTA pair, cta_group::2) walks tiles t, t+G, t+2G, ...
 #include "gemm_tc.h"
+
+#include <cstdlib>
 #include "ptx.cuh"
 
 #include <cuda_bf16.h>
@@ -169,8 +171,14 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t cta_rank = 0;
-    if constexpr (kCG == 2) cta_rank = ptx::cluster_ctarank();
+    // CTA-pair kernels may be launched in clusters of several pairs (ranks 2i, 2i+1 = pair i; the pairs of one cluster work
+    // on neighbouring tiles at the same time): cta_rank = rank inside the pair, pair_base = cluster rank of its leader
+    uint32_t cta_rank = 0, pair_base = 0;
+    if constexpr (kCG == 2) {
+        const uint32_t cr = ptx::cluster_ctarank();
+        cta_rank = cr & 1u;
+        pair_base = cr & ~1u;
+    }
     ptx::griddep_launch();  // the stream successor may start its prologue now (it blocks in its own griddep_wait)
 
     if (warp == EPI_WARPS && lane == 0) {
@@ -222,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                         ptx::mbar_arrive_expect_tx(&full[stage], C::A_BYTES + C::B_BYTES);
                     } else {
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * (C::A_BYTES + C::B_BYTES));
-                        else ptx::mbar_arrive_cluster(&full[stage], 0);
+                        else ptx::mbar_arrive_cluster(&full[stage], pair_base);
                     }
                     uint8_t* a_dst = sA + stage * C::A_BYTES;
                     uint8_t* b_dst = sB + stage * C::B_BYTES;
@@ -286,8 +294,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                             bdesc = ptx::make_smem_desc_sw128(b_base + k * 32, 0, 1024);
                             ptx::umma_f16<kCG>(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                         }
-                        ptx::umma_commit<kCG>(&empty[stage]);
-                        if (kb == kb1 - 1) ptx::umma_commit<kCG>(&tfull[as]);
+                        ptx::umma_commit<kCG>(&empty[stage], pair_base);
+                        if (kb == kb1 - 1) ptx::umma_commit<kCG>(&tfull[as], pair_base);
                     }
                     __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -368,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
                     __syncwarp();
                     if (lane == 0) {
                         if constexpr (kCG == 1) ptx::mbar_arrive(&tempty[as]);
-                        else ptx::mbar_arrive_cluster(&tempty[as], 0);
+                        else ptx::mbar_arrive_cluster(&tempty[as], pair_base);
                     }
                 }
                 epi_store<kRagged, kStream>(v, cin_cur, *cp, c_alpha, c_hs, cur_row0 + lane, cur_col0, cur_ok, mx);
@@ -426,7 +434,17 @@ int launch_variant(GemmGroup& g, int max_sms, cudaStream_t stream) {
     cfg.stream = stream;
     cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = kCG;
+    // CTA pairs per cluster (experiment, MPLU_GEMM_PAIRS_PER_CLUSTER = 1 / 2 / 4): pairs of one cluster take consecutive tiles
+    // = the same B columns and neighbouring A rows at the same time
+    int pairs = 1;
+    if (kCG == 2) {
+        static const int env_pairs = [] { const char* e = getenv("MPLU_GEMM_PAIRS_PER_CLUSTER"); return e ? atoi(e) : 1; }();
+        pairs = (env_pairs == 2 || env_pairs == 4) ? env_pairs : 1;
+        while (pairs > 1 && grid % (kCG * pairs) != 0) grid -= kCG;  // whole clusters only
+        if (grid < kCG * pairs) { pairs = 1; grid = grid < kCG ? kCG : grid; }
+        cfg.gridDim = dim3(grid);
+    }
+    attrs[0].val.clusterDim.x = kCG * pairs;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
     attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -166,8 +166,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 
 // Make `bar` (in every CTA of the pair when kCG==2) track completion of all MMAs issued so far by this thread.
+// pair_base: cluster rank of the pair's leader CTA (0 unless several pairs share one cluster)
 template <int kCG>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t pair_base = 0) {
     if constexpr (kCG == 1) {
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                      : "memory");
@@ -175,7 +176,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
         asm volatile(
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                 smem_u32(bar)),
-            "h"(static_cast<uint16_t>(3))
+            "h"(static_cast<uint16_t>(3u << pair_base))
             : "memory");
     }
 }
