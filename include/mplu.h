@@ -109,6 +109,13 @@ typedef struct mplu_options {
     int pair_ts;      /* MPLU_SCHED_LEFT, two lanes: 1 = the bulk lane's small panel solves U(k, cols) share a grouped launch with the
                          previous op's tall update when their column ranges are disjoint (fills that launch's tail instead of a
                          one-wave launch of their own); same products, same factors */
+    int update_pair;  /* MPLU_SCHED_LEFT, two lanes: 1 = when two consecutive updates k, k+1 of a block-column range are both
+                         available the bulk lane applies them in ONE pass (K = both panels' widths: half the fp32 C traffic per
+                         flop of an L2-bound kernel).  Same products; the two partial sums are added in TMEM instead of through
+                         C, so factors agree with update_pair = 0 to fp32 rounding, not bit for bit.  Measured: 2-3 % faster at
+                         n = 32768 (with side_sms_left = flow_ctas = 20), 4 % at n = 65536, same iteration counts up to kappa = 1e6;
+                         default 0 because the twice as long fp32 accumulation in the tensor core costs GMRES-IR up to 5x more
+                         Krylov steps on the kappa >= 1e7 systems of the condition-number sweep */
     int flow_merge_ctas; /* helpers that take inverse-merge tasks before main-list tasks; -1 (default) = a quarter of them */
 } mplu_options;
 

@@ -29,7 +29,7 @@ class Options(C.Structure):
     _fields_ = [("precision", C.c_int), ("nb", C.c_int), ("max_iters", C.c_int), ("tol", C.c_double),
                 ("gemm_variant", C.c_int), ("max_sms", C.c_int), ("a_exp", C.c_int), ("l_exp", C.c_int),
                 ("lookahead", C.c_int), ("side_sms", C.c_int), ("use_graph", C.c_int), ("pdl", C.c_int), ("group", C.c_int),
-                ("refinement", C.c_int), ("gmres_restart", C.c_int), ("gmres_tol", C.c_double), ("bf16_fallback", C.c_int), ("tile_ws", C.c_int), ("cg2_min_elems", C.c_int), ("side_sms_early", C.c_int), ("early_pct", C.c_int), ("tri_skip", C.c_int), ("late_pct", C.c_int), ("l2_persist", C.c_int), ("stream_host", C.c_int), ("schedule", C.c_int), ("eager", C.c_int), ("side_sms_left", C.c_int), ("stream_c", C.c_int), ("early_scale", C.c_int), ("fuse_w", C.c_int), ("fuse_ctas", C.c_int), ("lazy_touch", C.c_int), ("flow_w", C.c_int), ("flow_ctas", C.c_int), ("fp64_fallback", C.c_int), ("edge_nb", C.c_int), ("pair_ts", C.c_int), ("flow_merge_ctas", C.c_int)]
+                ("refinement", C.c_int), ("gmres_restart", C.c_int), ("gmres_tol", C.c_double), ("bf16_fallback", C.c_int), ("tile_ws", C.c_int), ("cg2_min_elems", C.c_int), ("side_sms_early", C.c_int), ("early_pct", C.c_int), ("tri_skip", C.c_int), ("late_pct", C.c_int), ("l2_persist", C.c_int), ("stream_host", C.c_int), ("schedule", C.c_int), ("eager", C.c_int), ("side_sms_left", C.c_int), ("stream_c", C.c_int), ("early_scale", C.c_int), ("fuse_w", C.c_int), ("fuse_ctas", C.c_int), ("lazy_touch", C.c_int), ("flow_w", C.c_int), ("flow_ctas", C.c_int), ("fp64_fallback", C.c_int), ("edge_nb", C.c_int), ("pair_ts", C.c_int), ("update_pair", C.c_int), ("flow_merge_ctas", C.c_int)]
 
 
 class Stats(C.Structure):

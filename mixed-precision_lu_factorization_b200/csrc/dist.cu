@@ -190,51 +190,54 @@ __global__ void residual_full_kernel(const double* __restrict__ b, const double*
     }
 }
 
-// s[t] += sum_{c in [c_lo, c_hi)} W_loc(row0 + t, c) * v[global col(c)]     t < nb   (fp32 factors, fp32 vector)
-// HBM-bound (4 bytes per element of the tile row).  grid (nb/512, ceil(span/128)); block 128 threads; a thread owns 4
-// consecutive rows (128-bit loads, 8 columns in flight) of a 128-column chunk and adds its partial sums atomically.
-__global__ void __launch_bounds__(128)
-tile_row_gemv_kernel(const float* __restrict__ W, long long ldw, int row0, int c_lo, int c_hi,
-                     const float* __restrict__ v, float* s, int nb, int Q, int q) {
-    __shared__ float vs[128];
-    const int a = c_lo + blockIdx.y * 128, b = min(c_hi, a + 128);
-    for (int c = a + threadIdx.x; c < b; c += 128) vs[c - a] = __ldg(v + ((long long)(c / nb) * Q + q) * nb + c % nb);
-    __syncthreads();
-    const int t = 4 * (blockIdx.x * 128 + threadIdx.x);
-    if (t >= nb) return;
-    const float4* wp = reinterpret_cast<const float4*>(W + row0 + t + (long long)a * ldw);
+// part[global row of r] += sum_{c < nb} W_loc(r, c0 + c) * v[c]   for the local rows r in [r0, r1)   (fp32 factors, fp32 vector)
+// One tile column of the local factors against the solution block that column multiplies: the right-looking half of the
+// block-cyclic triangular solves.  HBM-bound (4 bytes per element).  grid (ceil((r1-r0)/128), nb/128), 256 threads: a block
+// owns 128 rows x 128 columns, warp w the columns 16 w .. 16 w + 15, a lane 4 consecutive rows (128-bit loads, all 16 in
+// flight: a single tile -- the latency-critical call -- is then two memory round trips, not sixteen); the eight warps'
+// partial sums meet in shared memory and one warp adds them to `part` atomically (several columns' kernels may be adding to
+// the same rows from two streams).
+__global__ void __launch_bounds__(256)
+tile_col_gemv_kernel(const float* __restrict__ W, long long ldw, int r0, int r1, int c0, const float* __restrict__ v,
+                     float* part, int nb, int P, int p) {
+    __shared__ float4 red[8][32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cb = blockIdx.y * 128 + 16 * w;
+    const int r = r0 + 128 * blockIdx.x + 4 * lane;  // r0, r1 are multiples of nb (a multiple of 128): no ragged block
+    const float4* wp = reinterpret_cast<const float4*>(W + r + (long long)(c0 + cb) * ldw);
     const long long ld4 = ldw / 4;
+    float4 t[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) t[u] = __ldcs(wp + u * ld4);
+    float x[16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(v + cb) + u);
+        x[4 * u] = xv.x; x[4 * u + 1] = xv.y; x[4 * u + 2] = xv.z; x[4 * u + 3] = xv.w;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nc = b - a;
-    int c = 0;
-    for (; c + 8 <= nc; c += 8) {
-        float4 w[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldcs(wp + (long long)(c + u) * ld4);
+    for (int u = 0; u < 16; ++u) {
+        acc.x = fmaf(t[u].x, x[u], acc.x); acc.y = fmaf(t[u].y, x[u], acc.y);
+        acc.z = fmaf(t[u].z, x[u], acc.z); acc.w = fmaf(t[u].w, x[u], acc.w);
+    }
+    red[w][lane] = acc;
+    __syncthreads();
+    if (w == 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float x = vs[c + u];
-            acc.x = fmaf(w[u].x, x, acc.x); acc.y = fmaf(w[u].y, x, acc.y);
-            acc.z = fmaf(w[u].z, x, acc.z); acc.w = fmaf(w[u].w, x, acc.w);
+        for (int g = 1; g < 8; ++g) {
+            const float4 o = red[g][lane];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
         }
+        float* out = part + ((long long)(r / nb) * P + p) * nb + r % nb;
+        atomicAdd(out, acc.x); atomicAdd(out + 1, acc.y); atomicAdd(out + 2, acc.z); atomicAdd(out + 3, acc.w);
     }
-    for (; c < nc; ++c) {
-        const float4 w = __ldcs(wp + (long long)c * ld4);
-        const float x = vs[c];
-        acc.x = fmaf(w.x, x, acc.x); acc.y = fmaf(w.y, x, acc.y);
-        acc.z = fmaf(w.z, x, acc.z); acc.w = fmaf(w.w, x, acc.w);
-    }
-    atomicAdd(s + t, acc.x); atomicAdd(s + t + 1, acc.y); atomicAdd(s + t + 2, acc.z); atomicAdd(s + t + 3, acc.w);
 }
 
-// forward: rhs64[t] = r[k nb + t] - s[t];  backward: yk[t] -= s[t]
-__global__ void tile_rhs_fwd_kernel(const double* __restrict__ r, const float* __restrict__ s, double* rhs64, int nb) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nb) rhs64[t] = r[t] - (double)s[t];
-}
-__global__ void tile_rhs_bwd_kernel(const float* __restrict__ y, const float* __restrict__ s, float* out, int nb) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nb) out[t] = y[t] - s[t];
+// step counters of the tile sweeps: T forward sweeps start at step 0, T backward sweeps at step nblk
+__global__ void fill_ready_kernel(unsigned* ready, int T, unsigned nblk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * T) ready[i] = i < T ? 0u : nblk;
 }
 // x (+)= d
 __global__ void apply_correction_kernel(const float* __restrict__ d, double* x, int n, int accumulate) {
@@ -261,8 +264,11 @@ struct DRank {
     mplu_context* ctx = nullptr;   // options / status / small device words for the GEMM launches of this rank
     mplu_context* dctx = nullptr;  // nb x nb context that factors diagonal tiles
     cudaStream_t chain = nullptr, bulk = nullptr;
+    cudaStream_t hi = nullptr;  // greatest priority: the dependency chain of the triangular solves (owned by this struct)
     cudaEvent_t ev_tmp = nullptr, ev_chain = nullptr, ev_bulk = nullptr, ev_e1 = nullptr, ev_d = nullptr, ev_panel[2] = {nullptr, nullptr};
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kSolveRing = 8;
+    cudaEvent_t ev_sol[kSolveRing] = {}, ev_far[kSolveRing] = {};  // triangular solves: chain -> bulk (block solved), bulk -> chain
     int mt = 0, nt = 0;
     long long mloc = 0, nloc = 0;
     const double* A = nullptr;
@@ -279,8 +285,8 @@ struct DRank {
     float* Du32 = nullptr;
     Operand16 opWh, opLp[2], opUp[2], opInvL[2], opInvU[2];
     // refinement vectors (full length, replicated)
-    double *r = nullptr, *ax = nullptr, *rowsum = nullptr, *norms = nullptr, *rhs64 = nullptr, *anorm = nullptr;
-    float *yv = nullptr, *xv = nullptr, *sv = nullptr, *tmpf = nullptr;
+    double *r = nullptr, *ax = nullptr, *rowsum = nullptr, *norms = nullptr, *anorm = nullptr, *rhsbuf = nullptr;
+    float *yv = nullptr, *xv = nullptr, *part = nullptr;  // part: 2 x n partial sums of the two sweeps (global row order)
     unsigned* ready = nullptr;
 };
 
@@ -307,6 +313,9 @@ struct mplu_dist {
     std::vector<double*> stA, stb, stx;
     std::vector<size_t> stA_cap;
     int st_n = 0;
+    // the triangular solve of a single-rank process as a CUDA graph (captured on its second use for the current buffers)
+    cudaGraphExec_t solve_exec = nullptr;
+    int solve_uses = 0, solve_launches = 0;
 };
 
 namespace {
@@ -315,18 +324,20 @@ void free_rank_work(DRank& r) {
     cudaFree(r.W); cudaFree(r.Wh);
     for (int i = 0; i < 2; ++i) { cudaFree(r.Lp[i]); cudaFree(r.Up[i]); cudaFree(r.InvL[i]); cudaFree(r.InvU[i]); cudaFree(r.tsc[i]); }
     cudaFree(r.Dw); cudaFree(r.Dl32); cudaFree(r.Du32);
-    cudaFree(r.r); cudaFree(r.ax); cudaFree(r.rowsum); cudaFree(r.norms); cudaFree(r.rhs64); cudaFree(r.anorm);
-    cudaFree(r.yv); cudaFree(r.xv); cudaFree(r.sv); cudaFree(r.tmpf); cudaFree(r.ready);
+    cudaFree(r.r); cudaFree(r.ax); cudaFree(r.rowsum); cudaFree(r.norms); cudaFree(r.anorm); cudaFree(r.rhsbuf);
+    cudaFree(r.yv); cudaFree(r.xv); cudaFree(r.part); cudaFree(r.ready);
     r.W = nullptr; r.Wh = nullptr;
     for (int i = 0; i < 2; ++i) { r.Lp[i] = r.Up[i] = r.InvL[i] = r.InvU[i] = nullptr; r.tsc[i] = nullptr; }
     r.Dw = r.Dl32 = r.Du32 = nullptr;
-    r.r = r.ax = r.rowsum = r.norms = r.rhs64 = r.anorm = nullptr;
-    r.yv = r.xv = r.sv = r.tmpf = nullptr;
+    r.r = r.ax = r.rowsum = r.norms = r.anorm = r.rhsbuf = nullptr;
+    r.yv = r.xv = r.part = nullptr;
     r.ready = nullptr;
 }
 
 int alloc_rank_work(mplu_dist* d, DRank& r) {
     const int n = d->n, nb = d->nb, T = d->T;
+    if (d->solve_exec) { cudaGraphExecDestroy(d->solve_exec); d->solve_exec = nullptr; }
+    d->solve_uses = 0;
     free_rank_work(r);
     r.mt = tiles_local(T, d->P, r.p);
     r.nt = tiles_local(T, d->Q, r.q);
@@ -350,12 +361,11 @@ int alloc_rank_work(mplu_dist* d, DRank& r) {
     CK(cudaMalloc(&r.rowsum, n * sizeof(double)));
     CK(cudaMalloc(&r.norms, 2 * sizeof(double)));
     CK(cudaMalloc(&r.anorm, 2 * sizeof(double)));
-    CK(cudaMalloc(&r.rhs64, nb * sizeof(double)));
     CK(cudaMalloc(&r.yv, n * sizeof(float)));
     CK(cudaMalloc(&r.xv, n * sizeof(float)));
-    CK(cudaMalloc(&r.sv, nb * sizeof(float)));
-    CK(cudaMalloc(&r.tmpf, nb * sizeof(float)));
-    CK(cudaMalloc(&r.ready, sizeof(unsigned)));
+    CK(cudaMalloc(&r.part, 2 * (size_t)n * sizeof(float)));
+    CK(cudaMalloc(&r.rhsbuf, n * sizeof(double)));
+    CK(cudaMalloc(&r.ready, (2 * (size_t)T + 1) * sizeof(unsigned)));  // one step counter per tile sweep
     CKI(make_operand(&r.opWh, r.Wh, ml, nl, ml));
     for (int i = 0; i < 2; ++i) {
         CKI(make_operand(&r.opInvL[i], r.InvL[i], nb, nb, nb));
@@ -694,49 +704,195 @@ int enqueue_residual(mplu_dist* d, const std::vector<const double*>& b, const st
     return (int)cudaGetLastError();
 }
 
-// solve L U dvec = rhs with the distributed fp32 factors; result (float, full length) in r.xv of every rank
+// solve L U dvec = rhs with the distributed fp32 factors; result (float, full length) in r.xv of every rank.
+// Right-looking with look-ahead: as soon as the solution block of tile column k is known, the ranks that own tile column k
+// fold it into the partial sums `part` of the tile rows it multiplies -- the next D tile rows at once on the chain stream
+// (they are needed within D steps), every tile row beyond on the bulk stream (one tall HBM-bound GEMV, off the critical path;
+// the chain waits for it D + 1 steps later).  What is left on the dependency chain of a step is one all-reduce of nb
+// floats (in place on the tile row's slice of `part`: the ranks outside its process row hold zeros there) and the replicated
+// diagonal tile's sweep, which subtracts the reduced sums from its right-hand side itself.  (Round 1 formed each tile
+// row's dot products inside the step: memset + tile-row GEMV + all-reduce + right-hand-side kernel + 3 launches of the sweep
+// = 0.12 ms per tile step, 38 of the 52 ms the refinement took on 8 GPUs.)
+int solve_body(mplu_dist* d, const std::vector<const double*>& rhs);
+
 int enqueue_lu_solve(mplu_dist* d, const std::vector<const double*>& rhs) {
-    const int nb = d->nb, T = d->T, P = d->P, Q = d->Q;
-    auto chain_of = [](DRank& r) { return r.chain; };
-    auto sv_of = [](DRank& r) { return (void*)r.sv; };
+    static const int env_hi = [] { const char* e = getenv("MPLU_DIST_SOLVE_HI"); return e ? atoi(e) : 1; }();
+    static const int env_graph = [] { const char* e = getenv("MPLU_DIST_SOLVE_GRAPH"); return e ? atoi(e) : 0; }();
+    auto cs_of = [](DRank& r) { return env_hi ? r.hi : r.chain; };
+    for (auto& r : d->ranks) {
+        // earlier work of both streams (the previous solve's last GEMVs) is ordered before the accumulators are cleared
+        CK(cudaEventRecord(r.ev_bulk, r.bulk));
+        CK(cudaStreamWaitEvent(cs_of(r), r.ev_bulk, 0));
+        if (cs_of(r) != r.chain) {
+            CK(cudaEventRecord(r.ev_chain, r.chain));
+            CK(cudaStreamWaitEvent(cs_of(r), r.ev_chain, 0));
+        }
+    }
+    // One rank per process (the NCCL case): the ~1000 launches of a solve are the same every time -- replayed as a CUDA graph
+    // (the host could not enqueue them as fast as the device runs them: 9 API calls per 50 us step).  The right-hand side goes
+    // through a fixed buffer; the first solve on new buffers runs eagerly (NCCL sets its channels up outside a capture).
+    const bool graphable = env_graph && d->opts.use_graph && d->ranks.size() == 1 && cs_of(d->ranks[0]) != d->ranks[0].chain;
+    int rc = 0;
+    if (!graphable) {
+        rc = solve_body(d, rhs);
+    } else {
+        DRank& r = d->ranks[0];
+        cudaStream_t cs = cs_of(r);
+        CK(cudaMemcpyAsync(r.rhsbuf, rhs[0], (size_t)d->n * sizeof(double), cudaMemcpyDeviceToDevice, cs));
+        const std::vector<const double*> fixed{r.rhsbuf};
+        if (!d->solve_exec && d->solve_uses >= 1) {
+            const int before = d->kernel_launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+            rc = solve_body(d, fixed);
+            cudaError_t e = cudaStreamEndCapture(cs, &graph);
+            d->solve_launches = d->kernel_launches - before;
+            d->kernel_launches = before;
+            if (rc == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&d->solve_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != 0 || e != cudaSuccess) {  // not capturable here: launch by launch from now on
+                cudaGetLastError();
+                d->solve_exec = nullptr;
+                d->solve_uses = -(1 << 30);
+                rc = 0;
+            }
+        }
+        d->solve_uses++;
+        if (d->solve_exec) {
+            CK(cudaGraphLaunch(d->solve_exec, cs));
+            d->kernel_launches += d->solve_launches;
+        } else {
+            rc = solve_body(d, fixed);
+        }
+    }
+    if (rc) return rc;
+    for (auto& r : d->ranks) {  // the caller continues on the chain stream
+        if (cs_of(r) == r.chain) continue;
+        CK(cudaEventRecord(r.ev_chain, cs_of(r)));
+        CK(cudaStreamWaitEvent(r.chain, r.ev_chain, 0));
+    }
+    return (int)cudaGetLastError();
+}
+
+int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
+    const int nb = d->nb, T = d->T, P = d->P, Q = d->Q, n = d->n;
+    constexpr int RING = DRank::kSolveRing;
+    static const int env_depth = [] { const char* e = getenv("MPLU_DIST_SOLVE_DEPTH"); return e ? atoi(e) : 2; }();
+    const int D = env_depth < 1 ? 1 : (env_depth > RING - 2 ? RING - 2 : env_depth);
+    // The steps' dependency chain runs on a stream of the greatest priority: the sweep of a diagonal tile is a cooperative
+    // cluster launch whose CTAs need most of an SM each, and behind the thousands of small blocks of a tall GEMV on a stream of
+    // equal priority it would only start once that kernel drains.
+    static const int env_hi = [] { const char* e = getenv("MPLU_DIST_SOLVE_HI"); return e ? atoi(e) : 1; }();
+    static const int env_far = [] { const char* e = getenv("MPLU_DIST_SOLVE_FAR"); return e ? atoi(e) : 1; }();
+    auto cs_of = [](DRank& r) { return env_hi ? r.hi : r.chain; };
+    std::vector<char> far_on(d->ranks.size() * RING, 0), far_any(d->ranks.size(), 0);
+    static const int env_plain = [] { const char* e = getenv("MPLU_DIST_SOLVE_PLAIN"); return e ? atoi(e) : 1; }();
+    const int sweep_flags = SWEEP_PREPARED | (env_plain ? SWEEP_PLAIN_LAUNCH : 0);
+    for (auto& r : d->ranks) {
+        // once per solve instead of once per tile step: partial sums cleared, solution vectors NaN (the sweeps' consumers poll
+        // the data), the tile sweeps' step counters at their first step (0 forward, nb/128 backward)
+        CK(cudaMemsetAsync(r.part, 0, 2 * (size_t)n * sizeof(float), cs_of(r)));
+        CK(cudaMemsetAsync(r.yv, 0xFF, (size_t)n * sizeof(float), cs_of(r)));
+        CK(cudaMemsetAsync(r.xv, 0xFF, (size_t)n * sizeof(float), cs_of(r)));
+        fill_ready_kernel<<<(2 * T + 255) / 256, 256, 0, cs_of(r)>>>(r.ready, T, (unsigned)(nb / kDiagBlock));
+    }
+    // MPLU_DIST_SOLVE_TIMING=1 (development): event stamps around the phases of every step of rank 0's first eager solves
+    static const int env_timing = [] { const char* e = getenv("MPLU_DIST_SOLVE_TIMING"); return e ? atoi(e) : 0; }();
+    static int timed_solves = 0;
+    const bool timing = env_timing && timed_solves < 3 && T <= 128;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&]() {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, cs_of(d->ranks[0]));
+        tev.push_back(e);
+    };
     for (int sweep = 0; sweep < 2; ++sweep) {
         for (int kk = 0; kk < T; ++kk) {
             const int k = sweep == 0 ? kk : T - 1 - kk;
-            const int pk = k % P;
-            for (size_t i = 0; i < d->ranks.size(); ++i) {
-                DRank& r = d->ranks[i];
-                CK(cudaMemsetAsync(r.sv, 0, nb * sizeof(float), r.chain));
-                if (r.p == pk && r.nloc > 0 && kk > 0) {
-                    // forward: local tile columns with J < k; backward: J > k
-                    const int c_lo = sweep == 0 ? 0 : cnt_le(k, Q, r.q) * nb;
-                    const int c_hi = sweep == 0 ? cnt_lt(k, Q, r.q) * nb : (int)r.nloc;
-                    if (c_hi > c_lo) {
-                        const int span = c_hi - c_lo;
-                        dim3 grid((nb + 511) / 512, (span + 127) / 128);
-                        tile_row_gemv_kernel<<<grid, 128, 0, r.chain>>>(r.W, r.mloc, (k / P) * nb, c_lo, c_hi,
-                                                                         sweep == 0 ? r.yv : r.xv, r.sv, nb, Q, r.q);
-                        d->kernel_launches++;
-                    }
-                }
-            }
-            if (kk > 0) CKI(allreduce(d, 0, (size_t)nb, sv_of, chain_of));
+            const size_t off = (size_t)sweep * n + (size_t)k * nb;
+            stamp();
+            // the tall GEMVs that touch tile row k: the newest one belongs to the step D + 1 back
+            if (kk >= D + 1)
+                for (size_t i = 0; i < d->ranks.size(); ++i)
+                    if (far_on[i * RING + (kk - D - 1) % RING])
+                        CK(cudaStreamWaitEvent(cs_of(d->ranks[i]), d->ranks[i].ev_far[(kk - D - 1) % RING], 0));
+            stamp();
+            if (kk > 0) CKI(allreduce(d, 0, (size_t)nb, [&](DRank& r) { return (void*)(r.part + off); }, cs_of));
+            stamp();
             for (size_t i = 0; i < d->ranks.size(); ++i) {
                 DRank& r = d->ranks[i];
                 const float* Dk = r.Dw + (size_t)k * nb * nb;
                 const float* Li = r.Dl32 + (size_t)k * nb * kDiagBlock;
                 const float* Ui = r.Du32 + (size_t)k * nb * kDiagBlock;
-                if (sweep == 0) {
-                    tile_rhs_fwd_kernel<<<(nb + 255) / 256, 256, 0, r.chain>>>(rhs[i] + (size_t)k * nb, r.sv, r.rhs64, nb);
-                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, r.rhs64, r.yv + (size_t)k * nb, nullptr, nullptr, nullptr,
-                                        r.ready, 1, r.chain));
-                } else {
-                    tile_rhs_bwd_kernel<<<(nb + 255) / 256, 256, 0, r.chain>>>(r.yv + (size_t)k * nb, r.sv, r.tmpf, nb);
-                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, nullptr, r.tmpf, r.xv + (size_t)k * nb, nullptr, nullptr,
-                                        r.ready, 2, r.chain));
+                const float* sub = kk > 0 ? r.part + off : nullptr;
+                if (sweep == 0)
+                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, rhs[i] + (size_t)k * nb, r.yv + (size_t)k * nb, nullptr, nullptr,
+                                        nullptr, r.ready + k, 1, cs_of(r), sub, sweep_flags));
+                else
+                    CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, nullptr, r.yv + (size_t)k * nb, r.xv + (size_t)k * nb, nullptr,
+                                        nullptr, r.ready + T + k, 2, cs_of(r), sub, sweep_flags));
+                d->kernel_launches += 1;
+            }
+            stamp();
+            if (kk == T - 1) break;
+            // tile column k times its solution block, on the ranks of process column k mod Q
+            for (size_t i = 0; i < d->ranks.size(); ++i) {
+                DRank& r = d->ranks[i];
+                far_on[i * RING + kk % RING] = 0;
+                if (r.q != k % Q || r.mloc <= 0 || r.nloc <= 0) continue;
+                int near0, near1, far0, far1;  // local tile rows
+                if (sweep == 0) {  // global tile rows (k, k + D] and (k + D, T)
+                    near0 = cnt_le(k, P, r.p); near1 = cnt_le(std::min(k + D, T - 1), P, r.p);
+                    far0 = near1; far1 = r.mt;
+                } else {           // global tile rows [k - D, k) and [0, k - D)
+                    near0 = cnt_lt(std::max(k - D, 0), P, r.p); near1 = cnt_lt(k, P, r.p);
+                    far0 = 0; far1 = near0;
                 }
-                d->kernel_launches += 3;
+                const float* v = (sweep == 0 ? r.yv : r.xv) + (size_t)k * nb;
+                float* part = r.part + (size_t)sweep * n;
+                const int c0 = (k / Q) * nb;
+                auto gemv = [&](int t0, int t1, cudaStream_t st) {
+                    const int r0 = t0 * nb, r1 = t1 * nb;
+                    dim3 grid((unsigned)((r1 - r0) / 128), (unsigned)(nb / 128));
+                    tile_col_gemv_kernel<<<grid, 256, 0, st>>>(r.W, r.mloc, r0, r1, c0, v, part, nb, P, r.p);
+                    d->kernel_launches++;
+                };
+                if (near1 > near0) gemv(near0, near1, cs_of(r));
+                if (far1 > far0 && !env_far) gemv(far0, far1, cs_of(r));  // experiment: everything in stream order
+                else if (far1 > far0) {
+                    CK(cudaEventRecord(r.ev_sol[kk % RING], cs_of(r)));
+                    CK(cudaStreamWaitEvent(r.bulk, r.ev_sol[kk % RING], 0));
+                    gemv(far0, far1, r.bulk);
+                    CK(cudaEventRecord(r.ev_far[kk % RING], r.bulk));
+                    far_on[i * RING + kk % RING] = 1;
+                    far_any[i] = 1;
+                }
             }
         }
+    }
+    if (timing) {
+        ++timed_solves;
+        cudaStreamSynchronize(cs_of(d->ranks[0]));
+        double acc[4] = {0, 0, 0, 0};
+        const int steps = (int)tev.size() / 4;
+        for (int sidx = 0; sidx < steps; ++sidx)
+            for (int ph = 0; ph < 4; ++ph) {
+                const size_t a = 4 * sidx + ph, b = a + 1;
+                float ms = 0.f;
+                if (b < tev.size() && cudaEventElapsedTime(&ms, tev[a], tev[b]) == cudaSuccess) acc[ph] += ms;
+            }
+        fprintf(stderr, "[mplu dist solve timing] rank %d: %d steps, per step: far-wait %.1f us, all-reduce %.1f us, tile sweep %.1f us, "
+                        "near GEMV + far enqueue %.1f us\n", d->rank, steps, 1e3 * acc[0] / steps, 1e3 * acc[1] / steps, 1e3 * acc[2] / steps,
+                1e3 * acc[3] / steps);
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    for (size_t i = 0; i < d->ranks.size(); ++i) {  // the bulk stream's work belongs to this solve (and joins a capture)
+        DRank& r = d->ranks[i];
+        if (!far_any[i]) continue;
+        CK(cudaEventRecord(r.ev_bulk, r.bulk));
+        CK(cudaStreamWaitEvent(cs_of(r), r.ev_bulk, 0));
     }
     return (int)cudaGetLastError();
 }
@@ -770,8 +926,17 @@ static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
         CKI(mplu_create(&r.dctx, device));
         r.chain = r.ctx->stream;
         r.bulk = r.ctx->side;
+        {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&r.hi, cudaStreamNonBlocking, hi));
+        }
         cudaEvent_t* evs[] = {&r.ev_tmp, &r.ev_chain, &r.ev_bulk, &r.ev_e1, &r.ev_d, &r.ev_panel[0], &r.ev_panel[1]};
         for (auto e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (int i = 0; i < DRank::kSolveRing; ++i) {
+            CK(cudaEventCreateWithFlags(&r.ev_sol[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&r.ev_far[i], cudaEventDisableTiming));
+        }
     }
     return 0;
 }
@@ -831,10 +996,16 @@ void mplu_dist_destroy(mplu_dist* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
+    if (d->solve_exec) { cudaGraphExecDestroy(d->solve_exec); d->solve_exec = nullptr; }
     for (auto& r : d->ranks) {
         free_rank_work(r);
         cudaEvent_t evs[] = {r.ev_tmp, r.ev_chain, r.ev_bulk, r.ev_e1, r.ev_d, r.ev_panel[0], r.ev_panel[1]};
         for (auto e : evs) if (e) cudaEventDestroy(e);
+        for (int i = 0; i < DRank::kSolveRing; ++i) {
+            if (r.ev_sol[i]) cudaEventDestroy(r.ev_sol[i]);
+            if (r.ev_far[i]) cudaEventDestroy(r.ev_far[i]);
+        }
+        if (r.hi) cudaStreamDestroy(r.hi);
         mplu_destroy(r.ctx);
         mplu_destroy(r.dctx);
     }

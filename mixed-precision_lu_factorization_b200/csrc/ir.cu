@@ -113,7 +113,10 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
 // (U x = y, block i = 2*nblk-1-s).  A step is a left-looking dot-product form:
 //     acc = rhs_i - sum_{j solved before i} W(i,j) * sol_j ;   sol_i = inv(D_i) * acc
 // so a CTA streams the 128x128 fp32 tiles of its block row with 128-bit loads issued BEFORE it waits for sol_j, and
-// only the last tile + the 64 KiB inverse (prefetched into shared memory with cp.async) sit on the dependency chain.
+// only the last tile + the 64 KiB inverse sit on the dependency chain.  The inverse is simply the LAST ITEM of the tile
+// stream: it arrives in the same double-buffered registers (4 rows x 16 columns per thread) and is applied the way a tile
+// is, 64 FMAs per thread.  (Round 1 staged it in shared memory and every thread read a 64-entry row of it: 64 KiB through
+// the 128 B/clk shared-memory port = 512+ cycles on every one of the 2*n/128 links of the chain.)
 // Steps complete strictly in order; `ready` = number of completed steps is published with a release store and polled
 // with acquire loads.  CTA c owns steps c, c+G, ... in ascending order and the launch is cooperative (all CTAs are
 // co-resident), so every wait is on a step owned by a running CTA.  HBM-bound: 4*n^2 bytes per solve.
@@ -129,7 +132,7 @@ __global__ void residual_finish_kernel(const double* __restrict__ partial, int n
 // operands (which have slack) go through L2.
 constexpr int TSV_THREADS = 256;
 constexpr int DBS = kDiagBlock;
-constexpr int TSV_SMEM_BYTES = DBS * DBS * (int)sizeof(float);
+constexpr int TSV_SMEM_BYTES = 0;  // the inverse lives in registers
 constexpr int TSV_MB = 3;  // mailbox depth: blocks of the TSV_MB preceding steps arrive through DSMEM
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -153,21 +156,14 @@ __device__ __forceinline__ float ld_relaxed_f1(const float* p) {
 __device__ __forceinline__ void st_relaxed_f1(float* p, float v) {
     asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TSV_THREADS)
 lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
                 const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
                 double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end,
-                int use_mbox) {
-    extern __shared__ __align__(16) float s_inv[];  // 128 x 128 inverse of the step's diagonal block
+                int use_mbox, const float* __restrict__ sub) {
     __shared__ __align__(16) float s_part[8][DBS];
-    __shared__ float s_acc[DBS];
+    __shared__ __align__(16) float s_acc[DBS];
     __shared__ __align__(16) float mbox[2][TSV_MB][DBS];  // [owned-step parity][distance-1]: blocks of steps s-1 .. s-TSV_MB
     const int tid = threadIdx.x;
     const int rg = tid & 31, cg = tid >> 5;  // rows 4rg.., columns 16cg.. of a tile
@@ -190,28 +186,31 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
         const int t = back ? s - nblk : s;         // tiles in this block row
         const int i = back ? nblk - 1 - t : t;     // block row
         const float* solv = back ? xsol : ysol;
-        {   // prefetch the inverse (independent of every other step)
-            const float* inv = (back ? Uinv : Linv) + (long long)i * DBS * DBS;
-#pragma unroll
-            for (int u = 0; u < DBS * DBS / 4 / TSV_THREADS; ++u)
-                cp_async16(s_inv + 4 * (tid + u * TSV_THREADS), inv + 4 * (tid + u * TSV_THREADS));
-        }
+        const float* inv = (back ? Uinv : Linv) + (long long)i * DBS * DBS;  // 128 x 128, column-major
         // this row block's right-hand side: fetched NOW, long before the step's turn (loading it after the last operand
         // arrived put one L2/HBM latency on every link of the dependency chain)
-        float a_pre = __int_as_float(0x7fffffff);
+        float a_pre = __int_as_float(0x7fffffff), sub_pre = 0.f;
         if (tid < DBS) {
             const int row = i * DBS + tid;
+            if (sub) sub_pre = sub[row];  // one-sweep modes: what other block rows already contributed to this right-hand side
             if (back) a_pre = ld_relaxed_f1(ysol + row);  // may still be NaN = not solved yet: polled again below
             else a_pre = (row < n) ? static_cast<float>(rhs[row]) : 0.f;
         }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* wrow = W + (long long)i * DBS + 4 * rg;
         // 128-bit loads of this thread's 4 rows x 16 columns of tile tt
+        // (item t of the stream is the inverse of the diagonal block, same thread layout)
         auto load_tile = [&](float4 (&v)[16], int tt) {
-            const int j = back ? nblk - 1 - tt : tt;
-            const float* wp = wrow + ((long long)j * DBS + 16 * cg) * ldw;
+            if (tt < t) {
+                const int j = back ? nblk - 1 - tt : tt;
+                const float* wp = wrow + ((long long)j * DBS + 16 * cg) * ldw;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)q * ldw));
+                for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(wp + (long long)q * ldw));
+            } else {
+                const float* ip = inv + 4 * rg + 16 * cg * DBS;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = __ldcs(reinterpret_cast<const float4*>(ip + q * DBS));
+            }
         };
         // wait for the solution block tile tt multiplies (mailbox for the newest ones, else L2), then accumulate
         auto consume = [&](const float4 (&v)[16], int tt) {
@@ -250,83 +249,97 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
                 acc.w = fmaf(v[q].w, sv[q], acc.w);
             }
         };
-        // Two register buffers: the loads of tile tt+1 are in flight while the thread waits for the operand of tile tt.
+        // Everything after the last operand arrived is the dependency chain's link: cross-warp reduction of the tile
+        // products, the inverse (already in registers) applied to the 128 sums, cross-warp reduction, hand-off.
+        auto finish = [&](const float4 (&vi)[16]) {
+            *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = acc;
+            __syncthreads();
+            if (tid < DBS) {
+                const int row = i * DBS + tid;
+                float a = a_pre;
+                if (back && a != a) {  // y of this block row must be final (written by the forward sweep of this launch, or given)
+                    // y of block row i was solved at forward step i = s - (2t+1): near the turn it sits in a mailbox
+                    if (2 * t + 1 <= TSV_MB && delivered(2 * t + 1))
+                        for (int spin = 0; spin < (1 << 20) && a != a; ++spin) a = mb[2 * t][tid];
+                    for (int spin = 0; a != a; ++spin) {
+                        a = ld_relaxed_f1(ysol + row);
+                        if (a == a || seen >= (unsigned)nblk) break;
+                        if ((spin & 63) == 63) seen = ld_acquire_u32(ready);
+                    }
+                }
+                a -= sub_pre;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) a -= s_part[g][tid];
+                s_acc[tid] = a;
+            }
+            __syncthreads();
+            {   // sol_i = inv * acc: this thread's 4 rows x 16 columns of the inverse against s_acc[16 cg ..]
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 sa = *reinterpret_cast<const float4*>(&s_acc[16 * cg + 4 * q4]);
+                    const float sq[4] = {sa.x, sa.y, sa.z, sa.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 w = vi[4 * q4 + u];
+                        o.x = fmaf(w.x, sq[u], o.x);
+                        o.y = fmaf(w.y, sq[u], o.y);
+                        o.z = fmaf(w.z, sq[u], o.z);
+                        o.w = fmaf(w.w, sq[u], o.w);
+                    }
+                }
+                *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = o;
+            }
+            __syncthreads();
+            if (tid < DBS) {
+                float v = 0.f;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) v += s_part[g][tid];
+                const int row = i * DBS + tid;
+                if (use_mbox) {  // first of all: hand the block to the owners of the next steps through their shared memory
+#pragma unroll
+                    for (int d = 1; d <= TSV_MB; ++d)
+                        if (crank + d < csize && s + d < s_end) {
+                            unsigned remote;
+                            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(&mbox[kown & 1][d - 1][tid])), "r"(crank + d));
+                            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+                        }
+                }
+                if (back) {
+                    st_relaxed_f1(xsol + row, v);
+                    if (row < n) {
+                        if (d_out) d_out[row] = static_cast<double>(v);
+                        if (x_accum) x_accum[row] += static_cast<double>(v);
+                    }
+                } else {
+                    st_relaxed_f1(ysol + row, v);
+                }
+                // off the chain: every delivery is awaited (it may be one this step had no use for) and its slot re-armed
+                // (the next delivery into this parity's slots is for this CTA's step after next)
+#pragma unroll
+                for (int d = 1; d <= TSV_MB; ++d)
+                    if (delivered(d)) {
+                        float w = mb[d - 1][tid];
+                        for (int spin = 0; spin < (1 << 20) && w != w; ++spin) w = mb[d - 1][tid];
+                        mb[d - 1][tid] = __int_as_float(0x7fffffff);
+                    }
+            }
+        };
+        // Two register buffers: the loads of item tt+1 are in flight while the thread waits for the operand of tile tt.
         // (With a single buffer a CTA that had caught up with the sweep's frontier paid one HBM latency per tile on
         // top of the operand latency and set the pace of the whole dependency chain: 2.4 us per step.)
         {
             float4 va[16], vb[16];
-            if (t > 0) load_tile(va, 0);
+            load_tile(va, 0);
             for (int tt = 0; tt < t; tt += 2) {
-                if (tt + 1 < t) load_tile(vb, tt + 1);
+                load_tile(vb, tt + 1);  // tt + 1 <= t: a tile, or the inverse
                 consume(va, tt);
                 if (tt + 1 < t) {
-                    if (tt + 2 < t) load_tile(va, tt + 2);
+                    load_tile(va, tt + 2);
                     consume(vb, tt + 1);
                 }
             }
-        }
-        *reinterpret_cast<float4*>(&s_part[cg][4 * rg]) = acc;
-        cp_async_wait_all();
-        __syncthreads();
-        if (tid < DBS) {
-            const int row = i * DBS + tid;
-            float a = a_pre;
-            if (back && a != a) {  // y of this block row must be final (written by the forward sweep of this launch, or given)
-                // y of block row i was solved at forward step i = s - (2t+1): near the turn it sits in a mailbox
-                if (2 * t + 1 <= TSV_MB && delivered(2 * t + 1))
-                    for (int spin = 0; spin < (1 << 20) && a != a; ++spin) a = mb[2 * t][tid];
-                for (int spin = 0; a != a; ++spin) {
-                    a = ld_relaxed_f1(ysol + row);
-                    if (a == a || seen >= (unsigned)nblk) break;
-                    if ((spin & 63) == 63) seen = ld_acquire_u32(ready);
-                }
-            }
-            // every delivery is awaited (it may be one this step has no use for) and its slot re-armed
-#pragma unroll
-            for (int d = 1; d <= TSV_MB; ++d)
-                if (delivered(d)) {
-                    float w = mb[d - 1][tid];
-                    for (int spin = 0; spin < (1 << 20) && w != w; ++spin) w = mb[d - 1][tid];
-                    mb[d - 1][tid] = __int_as_float(0x7fffffff);
-                }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) a -= s_part[g][tid];
-            s_acc[tid] = a;
-        }
-        __syncthreads();
-        {   // sol_i = inv * acc : 2 threads per row, 64 columns each
-            const int r = tid & (DBS - 1), h = tid >> 7;
-            const float* ip = s_inv + r + (h * 64) * DBS;
-            float p0 = 0.f, p1 = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < 64; c += 2) {
-                p0 = fmaf(ip[c * DBS], s_acc[h * 64 + c], p0);
-                p1 = fmaf(ip[(c + 1) * DBS], s_acc[h * 64 + c + 1], p1);
-            }
-            s_part[h][r] = p0 + p1;
-        }
-        __syncthreads();
-        if (tid < DBS) {
-            const float v = s_part[0][tid] + s_part[1][tid];
-            const int row = i * DBS + tid;
-            if (back) {
-                st_relaxed_f1(xsol + row, v);
-                if (row < n) {
-                    if (d_out) d_out[row] = static_cast<double>(v);
-                    if (x_accum) x_accum[row] += static_cast<double>(v);
-                }
-            } else {
-                st_relaxed_f1(ysol + row, v);
-            }
-            if (use_mbox) {  // hand the block to the owners of the next steps through their shared memory
-#pragma unroll
-                for (int d = 1; d <= TSV_MB; ++d)
-                    if (crank + d < csize && s + d < s_end) {
-                        unsigned remote;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(&mbox[kown & 1][d - 1][tid])), "r"(crank + d));
-                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
-                    }
-            }
+            if (t & 1) finish(vb); else finish(va);
         }
         __syncthreads();
         if (tid == 0) {
@@ -357,17 +370,25 @@ int launch_residual(const double* A, long long lda, int n, const double* x, cons
 }
 
 namespace {
-__global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+// step counter + NaN fill of what the sweep produces (consumers poll the data), one launch
+__global__ void sweep_prep_kernel(unsigned* ready, unsigned v, float* y_fill, float* x_fill, int npad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *ready = v;
+    if (i < npad) {
+        if (y_fill) y_fill[i] = __int_as_float(0x7fffffff);
+        if (x_fill) x_fill[i] = __int_as_float(0x7fffffff);
+    }
+}
 }  // namespace
 
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st) {
-    return launch_lu_sweep(W, ldw, n, npad, Linv32, Uinv32, rhs, y, y + npad, d_out, x_accum, ready, 0, st);
+    return launch_lu_sweep(W, ldw, n, npad, Linv32, Uinv32, rhs, y, y + npad, d_out, x_accum, ready, 0, st, nullptr);
 }
 
 int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
-                    int mode, cudaStream_t st) {
+                    int mode, cudaStream_t st, const float* sub, int flags) {
     // the dynamic shared-memory opt-in and the co-residency limits are PER DEVICE: cached per device ordinal
     constexpr int kMaxDev = 64;
     static int s_max_grid[kMaxDev] = {}, s_max_grid_cl[kMaxDev] = {};
@@ -404,10 +425,10 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
     }
     int nblk = npad / DBS;
     int s_begin = mode == 2 ? nblk : 0, s_end = mode == 1 ? nblk : 2 * nblk;
-    set_u32_kernel<<<1, 1, 0, st>>>(ready, (unsigned)s_begin);
     // NaN-fill what this launch produces: consumers poll the data (mode 2 takes its right-hand side in ysol)
-    if (mode != 2) cudaMemsetAsync(ysol, 0xFF, (size_t)npad * sizeof(float), st);
-    if (mode != 1 && xsol) cudaMemsetAsync(xsol, 0xFF, (size_t)npad * sizeof(float), st);
+    if (!(flags & SWEEP_PREPARED))
+        sweep_prep_kernel<<<(npad + 255) / 256, 256, 0, st>>>(ready, (unsigned)s_begin, mode != 2 ? ysol : nullptr,
+                                                             (mode != 1 && xsol) ? xsol : nullptr, npad);
     int use_mbox = 0;
     int grid = nblk < max_grid ? nblk : max_grid;
     if (max_grid_cl >= CL && nblk >= CL) {
@@ -427,16 +448,25 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
     attrs[1].val.clusterDim.x = CL; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = use_mbox ? 2 : 1;
+    // SWEEP_PLAIN_LAUNCH (one sweep of a small tile, every step its own CTA, far fewer CTAs than SMs): no cooperative
+    // attribute.  A CTA only ever waits for steps owned by CTAs of lower index, and the hardware dispatches CTAs (clusters) in
+    // index order, so a waiting CTA never keeps the one it waits for off the machine.
+    if ((flags & SWEEP_PLAIN_LAUNCH) && mode != 0 && grid == nblk && grid <= 32) {
+        attrs[0] = attrs[1];
+        cfg.numAttrs = use_mbox ? 1 : 0;
+    }
     cudaError_t le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out,
-                                        x_accum, ready, s_begin, s_end, use_mbox);
+                                        x_accum, ready, s_begin, s_end, use_mbox, sub);
     if (le != cudaSuccess && use_mbox) {  // cooperative cluster launch not available: plain cooperative launch from now on
         cudaGetLastError();
         max_grid_cl = 0;
         use_mbox = 0;
         cfg.gridDim = dim3(nblk < max_grid ? nblk : max_grid);
+        attrs[0].id = cudaLaunchAttributeCooperative;
+        attrs[0].val.cooperative = 1;
         cfg.numAttrs = 1;
         le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out, x_accum, ready,
-                                s_begin, s_end, use_mbox);
+                                s_begin, s_end, use_mbox, sub);
     }
     return (int)le;
 }

@@ -1082,7 +1082,7 @@ int enqueue_factorization(mplu_context* c) {
 // applied from step k+1 on (its L panel is complete then).  Step j first brings block column j+1 up to date
 // (mandatory), then spends the rest of its share of the remaining update flops on the columns further right, nearest
 // first, one op per run of equally advanced columns.  An op applies update k to block columns [m0, m1).
-struct LeftOp { int step, k, m0, m1, mandatory; };
+struct LeftOp { int step, k, m0, m1, mandatory, kn = 1; };  // kn: consecutive updates k .. k+kn-1 applied in one pass
 
 // Block-column boundaries of the left-looking schedule: nb-wide, except that with opts.edge_nb the first and the last one are
 // narrower.  While the first diagonal tile is factored nothing else can run, and the last one has nothing left to overlap
@@ -1102,7 +1102,9 @@ std::vector<int> tile_bounds(int npad, int NB, int edge) {
     return tb;
 }
 
-std::vector<LeftOp> plan_left(const std::vector<int>& tb, bool eager) {
+// pair: an op may apply TWO consecutive updates (k, k+1) in one pass over the block columns (K = both panels' widths: the
+// tall update is bound by L2 traffic and its fp32 C read + write is a fifth of that at K = 2048, a tenth at 4096)
+std::vector<LeftOp> plan_left(const std::vector<int>& tb, bool eager, bool pair = false) {
     const int nt = (int)tb.size() - 1, npad = tb[nt];
     std::vector<LeftOp> ops;
     std::vector<int> done(nt > 0 ? nt : 1, 0);  // done[m]: block column m has received the updates k < done[m]
@@ -1117,8 +1119,10 @@ std::vector<LeftOp> plan_left(const std::vector<int>& tb, bool eager) {
     for (int j = 1; j + 1 < nt; ++j) {
         double spent = 0.0;
         for (int k = done[j + 1]; k < j; ++k) {
-            ops.push_back({j, k, j + 1, j + 2, 1});
+            const int kn = (pair && k + 1 < j) ? 2 : 1;
+            ops.push_back({j, k, j + 1, j + 2, 1, kn});
             spent += cost(k, j + 1, j + 2);
+            if (kn == 2) { ++k; spent += cost(k, j + 1, j + 2); }
         }
         done[j + 1] = j;
         const double share = eager ? remaining / (double)(nt - 1 - j) : 0.0;
@@ -1129,11 +1133,13 @@ std::vector<LeftOp> plan_left(const std::vector<int>& tb, bool eager) {
             const int d = done[m];
             int m1 = m + 1;
             while (m1 < nt && done[m1] == d) ++m1;
-            const int fit = (int)((share - spent) / cost(d, m, m + 1) + 0.5);
+            const int kn = (pair && d + 1 < j) ? 2 : 1;  // update d+1 is available too (its L panel is complete)
+            const double c1 = cost(d, m, m + 1) + (kn == 2 ? cost(d + 1, m, m + 1) : 0.0);
+            const int fit = (int)((share - spent) / c1 + 0.5);
             if (m1 - m > fit) m1 = m + (fit > 1 ? fit : 1);
-            ops.push_back({j, d, m, m1, 0});
-            spent += cost(d, m, m1);
-            for (int i = m; i < m1; ++i) done[i] = d + 1;
+            ops.push_back({j, d, m, m1, 0, kn});
+            spent += cost(d, m, m1) + (kn == 2 ? cost(d + 1, m, m1) : 0.0);
+            for (int i = m; i < m1; ++i) done[i] = d + kn;
         }
         remaining -= spent;
     }
@@ -1253,9 +1259,34 @@ int enqueue_factorization_left(mplu_context* c) {
         if (pend.have) { pend_ev.push_back(e); return 0; }
         return ev_record(c, e, bulk.st);
     };
-    auto apply = [&](int k, int m0, int m1) -> int {
+    auto apply = [&](int k, int m0, int m1, int kn = 1) -> int {
         const int k0 = tb[k], k1 = tb[k + 1], d0 = colb(m0), d1 = colb(m1);
         const int next_rows = colb(k + 2) - k1;  // tile row k+1 is what the next panel solve reads
+        if (kn == 2) {
+            // updates k and k+1 in one pass: U(k,.) -> update k on tile row k+1 only (its U(k+1,.) solve reads it) -> U(k+1,.)
+            // -> rows below tile row k+1 receive both updates from the two adjacent panels as ONE product with K = both widths
+            const int k2 = colb(k + 2);
+            CKI(launch_pending(nullptr, 0.0));
+            CKI(S.trsm_u(bulk, k0, k0, k1 - k0, d0, d1));
+            CKI(S.schur(bulk, k1, k2, d0, d1, k0, k1, k2 - k1, 0, k0 == 0));
+            CKI(S.trsm_u(bulk, k1, k1, k2 - k1, d0, d1));
+            if (k2 < npad) {
+                const bool timed = !c->trace && c->trail_count < mplu_context::kMaxTrail;
+                if (timed) {
+                    cudaEvent_t& e0 = c->trail_ev[2 * c->trail_count];
+                    if (!e0) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&c->trail_ev[2 * c->trail_count + 1])); }
+                    CKI(record_event(c, e0, bulk.st));
+                }
+                CKI(S.schur(bulk, k2, npad, d0, d1, k0, k2, colb(k + 3) - k2, 0, k0 == 0));
+                if (timed) {
+                    CKI(record_event(c, c->trail_ev[2 * c->trail_count + 1], bulk.st));
+                    c->trail_count++;
+                    c->trail_flops += 2.0 * (npad - k2) * (double)(d1 - d0) * (k2 - k0);
+                    c->trail_bytes += 8.0 * (npad - k2) * (double)(d1 - d0);
+                }
+            }
+            return 0;
+        }
         if (!pair_ts) {
             CKI(S.trsm_u(bulk, k0, k0, k1 - k0, d0, d1));
             return timed_schur(bulk, k1, d0, d1, k0, k1, next_rows);
@@ -1271,7 +1302,7 @@ int enqueue_factorization_left(mplu_context* c) {
         pend.bytes = 8.0 * (npad - k1) * (double)(d1 - d0);
         return 0;
     };
-    const std::vector<LeftOp> plan = plan_left(tb, c->opts.eager != 0);
+    const std::vector<LeftOp> plan = plan_left(tb, c->opts.eager != 0, two && c->opts.update_pair != 0);
     size_t pi = 0;
     for (int j = 1; j < nt; ++j) {
         const int c0 = tb[j], c1 = tb[j + 1], w = c1 - c0;
@@ -1319,10 +1350,10 @@ int enqueue_factorization_left(mplu_context* c) {
             // mandatory ops of this step (block column j+1 brought up to date), the event the chain lane's next step
             // waits for, then the eager ops (plan_left)
             for (; pi < plan.size() && plan[pi].step == j && plan[pi].mandatory; ++pi)
-                CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
+                CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1, plan[pi].kn));
             CKI(step_event(c, j + 1, EV_COL, &ev));
             CKI(record_after_pending(ev));
-            for (; pi < plan.size() && plan[pi].step == j; ++pi) CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1));
+            for (; pi < plan.size() && plan[pi].step == j; ++pi) CKI(apply(plan[pi].k, plan[pi].m0, plan[pi].m1, plan[pi].kn));
         }
         CKI(launch_pending(nullptr, 0.0));  // nothing stays pending across the wait for this step's GETRF
         CKI(mark(c, 6000 + j, bulk.st));
@@ -1455,7 +1486,7 @@ int factor_impl(mplu_context* c, int n, const double* dA, long long lda) {
     const std::vector<long long> key = {
         n, npad, effective_nb(c, npad), o.precision, o.gemm_variant, o.max_sms, o.lookahead, o.side_sms, o.a_exp, o.l_exp,
         o.pdl, o.group, o.tile_ws, o.cg2_min_elems, o.side_sms_early, o.early_pct, o.late_pct, o.tri_skip, o.l2_persist,
-        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, o.edge_nb, o.pair_ts, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
+        o.schedule, o.eager, o.side_sms_left, o.stream_c, o.fuse_w, o.fuse_ctas, o.flow_w, o.flow_ctas, o.flow_merge_ctas, o.edge_nb, o.pair_ts, o.update_pair, (long long)c->flow_prof_launch, (long long)early, (long long)lazy, (long long)c->marks_on,
         (long long)reinterpret_cast<uintptr_t>(c->W), (long long)reinterpret_cast<uintptr_t>(c->tile ? c->tile->W : nullptr)};
     const bool hit = use_graph && c->graph_exec && key == c->gkey;
     if (!hit) {
@@ -1707,6 +1738,7 @@ void mplu_default_options(mplu_options* o) {
     o->fp64_fallback = 1;
     o->edge_nb = 0;
     o->pair_ts = 0;
+    o->update_pair = 0;
 }
 
 int mplu_create(mplu_context** out, int device) {
@@ -2128,11 +2160,14 @@ int mplu_debug_tile_bounds(int n, int nb, int edge, int* out, int max) {
     return (int)tb.size();
 }
 // the plan for those boundaries (5 ints per op: step, k, m0, m1, mandatory)
+// eager: bit 0 = eager updates, bit 1 = paired updates (an op with kn = 2 is reported as its two updates k and k+1)
 int mplu_debug_plan_left_edge(int n, int nb, int edge, int eager, int* out, int max) {
     if (n <= 0 || nb < kDiagBlock) return MPLU_E_ARG;
     const int npad = ((n + kDiagBlock - 1) / kDiagBlock) * kDiagBlock;
     nb = (nb / kDiagBlock) * kDiagBlock;
-    const std::vector<LeftOp> ops = plan_left(tile_bounds(npad, nb > npad ? npad : nb, edge), eager != 0);
+    std::vector<LeftOp> ops;
+    for (const LeftOp& o : plan_left(tile_bounds(npad, nb > npad ? npad : nb, edge), (eager & 1) != 0, (eager & 2) != 0))
+        for (int i = 0; i < o.kn; ++i) ops.push_back({o.step, o.k + i, o.m0, o.m1, o.mandatory, 1});
     if (out && (int)ops.size() <= max)
         for (size_t i = 0; i < ops.size(); ++i) {
             out[5 * i] = ops[i].step; out[5 * i + 1] = ops[i].k; out[5 * i + 2] = ops[i].m0; out[5 * i + 3] = ops[i].m1; out[5 * i + 4] = ops[i].mandatory;

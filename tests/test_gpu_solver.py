@@ -133,7 +133,7 @@ def test_streamed_host_path_gives_bit_identical_factors(mplu, oracle, n, nb, pin
     try:
         outs = []
         for stream_host in (1, 0, 1):
-            st = s.gesv_host_ptr(n, pA, n, pb, px, mplu.default_options(nb=nb, stream_host=stream_host))
+            st = s.gesv_host_ptr(n, pA, n, pb, px, mplu.default_options(nb=nb, stream_host=stream_host, update_pair=0))
             assert st.converged == 1 and st.status_bits == 0 and st.h2d_ms > 0
             xs = hx.numpy().copy() if pinned else x.copy()
             outs.append((s.factors(n).clone(), xs, st.iters))
@@ -371,7 +371,7 @@ def test_schedule_options_do_not_change_the_arithmetic(mplu, oracle):
             dict(schedule=1, pair_ts=1), dict(schedule=1, pair_ts=1, eager=0, use_graph=0), dict(schedule=1, pair_ts=1, flow_w=0),
             dict(schedule=1, pair_ts=1, flow_w=0, fuse_w=0, lazy_touch=0))
         for kw in right + left:
-            x, st = s.gesv(dA, db, mplu.default_options(nb=512, **kw))
+            x, st = s.gesv(dA, db, mplu.default_options(nb=512, update_pair=0, **kw))  # paired updates: test_paired_updates
             LU = s.factors(n)
             assert st.converged == 1
             flow_w = kw.get("flow_w", 2048)
@@ -423,6 +423,36 @@ def test_fused_getrf_matches_the_launch_per_product_path(mplu, oracle, n, nb, fu
         # the 16-bit inverse of a diagonal block can round the other way: one fp16 ulp of a multiplier
         assert dL <= (2.0 ** -10 if precision == 0 else 2.0 ** -7) * torch.tril(LU0, -1).abs().max().item(), dL
         assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("n,nb", [(8192, 1024), (4096, 512), (6000, 1024), (16384, 2048)])
+@pytest.mark.parametrize("kw", [dict(), dict(lazy_touch=0), dict(use_graph=0, precision=1), dict(edge_nb=256, eager=0)])
+def test_paired_updates(mplu, oracle, n, nb, kw):
+    """opts.update_pair: two consecutive rank-nb updates of a block-column range applied as ONE product over both panels
+    (K = 2 nb).  Same 16-bit products; the two partial sums meet in the TMEM accumulator instead of in fp32 C, so the factors
+    agree with the one-update-per-pass schedule to fp32 rounding of the entries (not bit for bit), the refined solution to
+    fp64 accuracy, and repeated runs are bit-identical."""
+    import torch
+    A, b = mplu.generate(n, seed=9)
+    s = mplu.Solver(0)
+    try:
+        x0, st0 = s.gesv(A, b, mplu.default_options(nb=nb, update_pair=0, **kw))
+        LU0 = s.factors(n).clone()
+        LU1 = None
+        for rep in range(2):
+            x1, st1 = s.gesv(A, b, mplu.default_options(nb=nb, update_pair=1, **kw))
+            assert st1.converged == 1 and st1.status_bits == 0 and st1.iters <= st0.iters + 1
+            assert st1.trailing_launches < st0.trailing_launches  # fewer, longer update passes
+            F = s.factors(n)
+            if LU1 is None:
+                LU1 = F.clone()
+            assert torch.equal(F, LU1)
+        tol = 2.0 ** -8 if kw.get("precision", 0) == 0 else 2.0 ** -5  # a 16-bit shadow may round the other way
+        assert (LU1 - LU0).abs().max().item() <= tol * LU0.abs().max().item()
+        assert float((x1 - 1).abs().max()) < 1e-11 and float((x1 - x0).abs().max()) < 1e-11
+        assert st1.backward_error <= 2 * n * EPS
     finally:
         s.close()
 

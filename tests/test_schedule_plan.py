@@ -54,7 +54,7 @@ def bounds(mplu, n, nb, edge):
 
 @pytest.mark.parametrize("n,nb,edge", [(32768, 2048, 1024), (32768, 2048, 512), (9000, 1152, 384), (4096, 512, 128), (8192, 1024, 512),
                                        (2304, 512, 256), (32768, 2048, 0), (1024, 512, 256), (33000, 2048, 1024)])
-@pytest.mark.parametrize("eager", [0, 1])
+@pytest.mark.parametrize("eager", [0, 1, 2, 3])  # bit 1: paired updates (opts.update_pair), reported as their two updates
 def test_left_plan_with_narrow_edge_tiles(mplu, n, nb, edge, eager):
     """opts.edge_nb: boundaries stay multiples of 128, no block column is wider than nb, the first and last are `edge` wide
     whenever the matrix has at least four nb-wide block columns, and the plan on those boundaries keeps its invariants."""
@@ -110,3 +110,4 @@ def test_ctypes_mirrors_match_the_library(mplu):
     assert (o.stream_host, o.schedule, o.side_sms_left, o.eager, o.stream_c, o.early_scale) == (1, 1, 16, 1, 1, 0)
     assert (o.fuse_w, o.fuse_ctas, o.lazy_touch) == (512, 8, 1)
     assert (o.flow_w, o.flow_ctas, o.flow_merge_ctas) == (2048, 16, -1)
+    assert (o.edge_nb, o.pair_ts, o.update_pair) == (0, 0, 0)

@@ -71,7 +71,8 @@ CASES = [(32768, 2048), (2304, 512), (1000, 256), (1536, 512), (640, 512), (9000
 @pytest.mark.parametrize("n,nb", CASES)
 @pytest.mark.parametrize("kw", [dict(schedule=1), dict(schedule=1, eager=0), dict(schedule=1, lookahead=0), dict(schedule=0),
                                 dict(schedule=0, lookahead=0), dict(schedule=0, group=0), dict(schedule=1, group=0),
-                                dict(schedule=1, pair_ts=1), dict(schedule=1, pair_ts=1, eager=0)])
+                                dict(schedule=1, pair_ts=1), dict(schedule=1, pair_ts=1, eager=0),
+                                dict(schedule=1, update_pair=1), dict(schedule=1, update_pair=1, eager=0, pair_ts=1)])
 def test_schedule_is_race_free(mplu, n, nb, kw):
     ops = trace(mplu, n, nb, **kw)
     launches, ordered = check(merge_groups(ops))
@@ -86,7 +87,7 @@ def test_schedule_is_race_free(mplu, n, nb, kw):
 
 
 @pytest.mark.parametrize("n,nb,edge", [(32768, 2048, 1024), (9000, 1152, 384), (4096, 512, 128), (8192, 1024, 512), (2304, 512, 256)])
-@pytest.mark.parametrize("kw", [dict(), dict(eager=0), dict(group=0), dict(pair_ts=1)])
+@pytest.mark.parametrize("kw", [dict(), dict(eager=0), dict(group=0), dict(pair_ts=1), dict(update_pair=1)])
 def test_schedule_with_narrow_edge_tiles_is_race_free(mplu, n, nb, edge, kw):
     """opts.edge_nb: the first and last block column narrower than nb (non-uniform boundaries through the whole left-looking
     schedule): same vector-clock check, and every 128-leaf still factored exactly once."""
