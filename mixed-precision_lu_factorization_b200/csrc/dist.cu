@@ -239,6 +239,26 @@ __global__ void fill_ready_kernel(unsigned* ready, int T, unsigned nblk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 2 * T) ready[i] = i < T ? 0u : nblk;
 }
+// ---- peer exchange of the triangular solves' partial sums (NCCL mode; replaces one ncclAllReduce of nb floats per tile step)
+// Every rank owns one exchange buffer mapped into all its peers (CUDA IPC over NVLink): kPxFlagWords flag words, then slots
+// of nb floats.  Slot / flag index of (sweep, tile row k, process column q) = (sweep T + k) Q + q.  A rank of the tile
+// row's process row stores its nb partial sums into that slot of EVERY rank and then raises the slot's flag to the solve's
+// epoch; every rank's tile sweep (lu_solve_kernel, csrc/ir.cu: SweepPx) waits for the Q flags of the step and adds the Q slots
+// up itself.  One NVLink store + one flag per hop instead of a collective launch: the ranks' only per-step synchronisation.
+constexpr size_t kPxDataFloats = (size_t)16 << 20;
+
+__global__ void __launch_bounds__(256)
+px_send_kernel(const float* __restrict__ src, float* const* __restrict__ peers, size_t slot, int nb, unsigned epoch) {
+    float* base = peers[blockIdx.x];  // one block per destination rank
+    float4* dst = reinterpret_cast<float4*>(base + kPxFlagWords + slot * nb);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = threadIdx.x; i < nb / 4; i += blockDim.x) dst[i] = s4[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<unsigned*>(base) + slot), "r"(epoch) : "memory");
+}
+
 // x (+)= d
 __global__ void apply_correction_kernel(const float* __restrict__ d, double* x, int n, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,11 +284,11 @@ struct DRank {
     mplu_context* ctx = nullptr;   // options / status / small device words for the GEMM launches of this rank
     mplu_context* dctx = nullptr;  // nb x nb context that factors diagonal tiles
     cudaStream_t chain = nullptr, bulk = nullptr;
-    cudaStream_t hi = nullptr;  // greatest priority: the dependency chain of the triangular solves (owned by this struct)
+    cudaStream_t hi = nullptr, hi2 = nullptr;  // greatest priority: the triangular solves' tile sweeps / their near GEMVs and sends (owned by this struct)
     cudaEvent_t ev_tmp = nullptr, ev_chain = nullptr, ev_bulk = nullptr, ev_e1 = nullptr, ev_d = nullptr, ev_panel[2] = {nullptr, nullptr};
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};
     static constexpr int kSolveRing = 8;
-    cudaEvent_t ev_sol[kSolveRing] = {}, ev_far[kSolveRing] = {};  // triangular solves: chain -> bulk (block solved), bulk -> chain
+    cudaEvent_t ev_sol[kSolveRing] = {}, ev_far[kSolveRing] = {}, ev_swp[kSolveRing] = {};  // triangular solves: chain -> bulk (block solved), bulk -> chain
     int mt = 0, nt = 0;
     long long mloc = 0, nloc = 0;
     const double* A = nullptr;
@@ -316,6 +336,12 @@ struct mplu_dist {
     // the triangular solve of a single-rank process as a CUDA graph (captured on its second use for the current buffers)
     cudaGraphExec_t solve_exec = nullptr;
     int solve_uses = 0, solve_launches = 0;
+    // peer exchange of the solves' partial sums (NCCL mode): own buffer, the peers' mappings, device table of all of them
+    bool px_on = false;
+    float* px_mine = nullptr;
+    std::vector<void*> px_opened;
+    float** px_peers = nullptr;
+    unsigned px_epoch = 0;
 };
 
 namespace {
@@ -731,7 +757,7 @@ int enqueue_lu_solve(mplu_dist* d, const std::vector<const double*>& rhs) {
     // One rank per process (the NCCL case): the ~1000 launches of a solve are the same every time -- replayed as a CUDA graph
     // (the host could not enqueue them as fast as the device runs them: 9 API calls per 50 us step).  The right-hand side goes
     // through a fixed buffer; the first solve on new buffers runs eagerly (NCCL sets its channels up outside a capture).
-    const bool graphable = env_graph && d->opts.use_graph && d->ranks.size() == 1 && cs_of(d->ranks[0]) != d->ranks[0].chain;
+    const bool graphable = env_graph && !d->px_on && d->opts.use_graph && d->ranks.size() == 1 && cs_of(d->ranks[0]) != d->ranks[0].chain;  // (the exchange's epoch is a kernel argument)
     int rc = 0;
     if (!graphable) {
         rc = solve_body(d, rhs);
@@ -779,14 +805,22 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
     constexpr int RING = DRank::kSolveRing;
     static const int env_depth = [] { const char* e = getenv("MPLU_DIST_SOLVE_DEPTH"); return e ? atoi(e) : 2; }();
     const int D = env_depth < 1 ? 1 : (env_depth > RING - 2 ? RING - 2 : env_depth);
-    // The steps' dependency chain runs on a stream of the greatest priority: the sweep of a diagonal tile is a cooperative
-    // cluster launch whose CTAs need most of an SM each, and behind the thousands of small blocks of a tall GEMV on a stream of
-    // equal priority it would only start once that kernel drains.
+    // The steps' dependency chain runs on streams of the greatest priority: the sweep of a diagonal tile is a cluster launch
+    // whose CTAs need most of an SM each, and behind the thousands of small blocks of a tall GEMV on a stream of equal priority
+    // it would only start once that kernel drains.
     static const int env_hi = [] { const char* e = getenv("MPLU_DIST_SOLVE_HI"); return e ? atoi(e) : 1; }();
     static const int env_far = [] { const char* e = getenv("MPLU_DIST_SOLVE_FAR"); return e ? atoi(e) : 1; }();
-    auto cs_of = [](DRank& r) { return env_hi ? r.hi : r.chain; };
-    std::vector<char> far_on(d->ranks.size() * RING, 0), far_any(d->ranks.size(), 0);
     static const int env_plain = [] { const char* e = getenv("MPLU_DIST_SOLVE_PLAIN"); return e ? atoi(e) : 1; }();
+    auto cs_of = [](DRank& r) { return env_hi ? r.hi : r.chain; };
+    // Partial sums of a tile row reach every rank through ncclAllReduce (default) or, with MPLU_DIST_PEER_EXCHANGE=1, through
+    // peer memory (px_send_kernel -> the sweep's own wait).  With the peer exchange the sweeps have the stream cs to
+    // themselves: sweep k+1 is launched behind sweep k, is resident (tile loads under way) and polling its slots while the
+    // GEMVs and sends of step k run on the stream gs.
+    const bool px = d->px_on && !d->local_mode && d->ranks.size() == 1 && !d->solve_exec && env_hi && 2 * (size_t)T * Q <= kPxFlagWords &&
+                    2 * (size_t)T * Q * nb <= kPxDataFloats;
+    if (px) ++d->px_epoch;
+    auto gs_of = [&](DRank& r) { return px ? r.hi2 : cs_of(r); };
+    std::vector<char> far_on(d->ranks.size() * RING, 0), far_any(d->ranks.size(), 0);
     const int sweep_flags = SWEEP_PREPARED | (env_plain ? SWEEP_PLAIN_LAUNCH : 0);
     for (auto& r : d->ranks) {
         // once per solve instead of once per tile step: partial sums cleared, solution vectors NaN (the sweeps' consumers poll
@@ -795,47 +829,59 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
         CK(cudaMemsetAsync(r.yv, 0xFF, (size_t)n * sizeof(float), cs_of(r)));
         CK(cudaMemsetAsync(r.xv, 0xFF, (size_t)n * sizeof(float), cs_of(r)));
         fill_ready_kernel<<<(2 * T + 255) / 256, 256, 0, cs_of(r)>>>(r.ready, T, (unsigned)(nb / kDiagBlock));
+        if (gs_of(r) != cs_of(r)) {
+            CK(cudaEventRecord(r.ev_swp[RING - 1], cs_of(r)));
+            CK(cudaStreamWaitEvent(gs_of(r), r.ev_swp[RING - 1], 0));
+        }
     }
-    // MPLU_DIST_SOLVE_TIMING=1 (development): event stamps around the phases of every step of rank 0's first eager solves
+    // MPLU_DIST_SOLVE_TIMING=1 (development): the first hosted rank's average time per tile step of its first eager solves
     static const int env_timing = [] { const char* e = getenv("MPLU_DIST_SOLVE_TIMING"); return e ? atoi(e) : 0; }();
     static int timed_solves = 0;
-    const bool timing = env_timing && timed_solves < 3 && T <= 128;
-    std::vector<cudaEvent_t> tev;
-    auto stamp = [&]() {
-        if (!timing) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, cs_of(d->ranks[0]));
-        tev.push_back(e);
-    };
+    const bool timing = env_timing && timed_solves < 3;
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    if (timing) {
+        CK(cudaEventCreate(&tev[0])); CK(cudaEventCreate(&tev[1]));
+        CK(cudaEventRecord(tev[0], cs_of(d->ranks[0])));
+    }
     for (int sweep = 0; sweep < 2; ++sweep) {
         for (int kk = 0; kk < T; ++kk) {
             const int k = sweep == 0 ? kk : T - 1 - kk;
             const size_t off = (size_t)sweep * n + (size_t)k * nb;
-            stamp();
             // the tall GEMVs that touch tile row k: the newest one belongs to the step D + 1 back
             if (kk >= D + 1)
                 for (size_t i = 0; i < d->ranks.size(); ++i)
                     if (far_on[i * RING + (kk - D - 1) % RING])
-                        CK(cudaStreamWaitEvent(cs_of(d->ranks[i]), d->ranks[i].ev_far[(kk - D - 1) % RING], 0));
-            stamp();
-            if (kk > 0) CKI(allreduce(d, 0, (size_t)nb, [&](DRank& r) { return (void*)(r.part + off); }, cs_of));
-            stamp();
+                        CK(cudaStreamWaitEvent(gs_of(d->ranks[i]), d->ranks[i].ev_far[(kk - D - 1) % RING], 0));
+            if (kk > 0 && px) {
+                DRank& r = d->ranks[0];
+                if (r.p == k % P) {
+                    px_send_kernel<<<d->nranks, 256, 0, gs_of(r)>>>(r.part + off, d->px_peers, ((size_t)sweep * T + k) * Q + r.q, nb, d->px_epoch);
+                    d->kernel_launches++;
+                }
+            } else if (kk > 0) {
+                CKI(allreduce(d, 0, (size_t)nb, [&](DRank& r) { return (void*)(r.part + off); }, cs_of));
+            }
             for (size_t i = 0; i < d->ranks.size(); ++i) {
                 DRank& r = d->ranks[i];
                 const float* Dk = r.Dw + (size_t)k * nb * nb;
                 const float* Li = r.Dl32 + (size_t)k * nb * kDiagBlock;
                 const float* Ui = r.Du32 + (size_t)k * nb * kDiagBlock;
-                const float* sub = kk > 0 ? r.part + off : nullptr;
+                const bool fused = px && kk > 0;  // the sweep itself waits for the peers' slots and adds them up
+                const float* sub = (kk > 0 && !fused) ? r.part + off : nullptr;
+                const SweepPx spx{d->px_mine, ((unsigned long long)sweep * T + k) * Q, Q, nb, d->px_epoch};
+                const SweepPx* pxp = fused ? &spx : nullptr;
                 if (sweep == 0)
                     CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, rhs[i] + (size_t)k * nb, r.yv + (size_t)k * nb, nullptr, nullptr,
-                                        nullptr, r.ready + k, 1, cs_of(r), sub, sweep_flags));
+                                        nullptr, r.ready + k, 1, cs_of(r), sub, sweep_flags, pxp));
                 else
                     CKI(launch_lu_sweep(Dk, nb, nb, nb, Li, Ui, nullptr, r.yv + (size_t)k * nb, r.xv + (size_t)k * nb, nullptr,
-                                        nullptr, r.ready + T + k, 2, cs_of(r), sub, sweep_flags));
+                                        nullptr, r.ready + T + k, 2, cs_of(r), sub, sweep_flags, pxp));
                 d->kernel_launches += 1;
+                if (gs_of(r) != cs_of(r) && kk < T - 1) {  // the GEMVs of this step read the block just solved
+                    CK(cudaEventRecord(r.ev_swp[kk % (RING - 1)], cs_of(r)));
+                    CK(cudaStreamWaitEvent(gs_of(r), r.ev_swp[kk % (RING - 1)], 0));
+                }
             }
-            stamp();
             if (kk == T - 1) break;
             // tile column k times its solution block, on the ranks of process column k mod Q
             for (size_t i = 0; i < d->ranks.size(); ++i) {
@@ -859,10 +905,10 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
                     tile_col_gemv_kernel<<<grid, 256, 0, st>>>(r.W, r.mloc, r0, r1, c0, v, part, nb, P, r.p);
                     d->kernel_launches++;
                 };
-                if (near1 > near0) gemv(near0, near1, cs_of(r));
-                if (far1 > far0 && !env_far) gemv(far0, far1, cs_of(r));  // experiment: everything in stream order
+                if (near1 > near0) gemv(near0, near1, gs_of(r));
+                if (far1 > far0 && !env_far) gemv(far0, far1, gs_of(r));  // experiment: everything in stream order
                 else if (far1 > far0) {
-                    CK(cudaEventRecord(r.ev_sol[kk % RING], cs_of(r)));
+                    CK(cudaEventRecord(r.ev_sol[kk % RING], gs_of(r)));
                     CK(cudaStreamWaitEvent(r.bulk, r.ev_sol[kk % RING], 0));
                     gemv(far0, far1, r.bulk);
                     CK(cudaEventRecord(r.ev_far[kk % RING], r.bulk));
@@ -874,22 +920,20 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
     }
     if (timing) {
         ++timed_solves;
-        cudaStreamSynchronize(cs_of(d->ranks[0]));
-        double acc[4] = {0, 0, 0, 0};
-        const int steps = (int)tev.size() / 4;
-        for (int sidx = 0; sidx < steps; ++sidx)
-            for (int ph = 0; ph < 4; ++ph) {
-                const size_t a = 4 * sidx + ph, b = a + 1;
-                float ms = 0.f;
-                if (b < tev.size() && cudaEventElapsedTime(&ms, tev[a], tev[b]) == cudaSuccess) acc[ph] += ms;
-            }
-        fprintf(stderr, "[mplu dist solve timing] rank %d: %d steps, per step: far-wait %.1f us, all-reduce %.1f us, tile sweep %.1f us, "
-                        "near GEMV + far enqueue %.1f us\n", d->rank, steps, 1e3 * acc[0] / steps, 1e3 * acc[1] / steps, 1e3 * acc[2] / steps,
-                1e3 * acc[3] / steps);
-        for (auto e : tev) cudaEventDestroy(e);
+        CK(cudaEventRecord(tev[1], cs_of(d->ranks[0])));
+        CK(cudaEventSynchronize(tev[1]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tev[0], tev[1]);
+        fprintf(stderr, "[mplu dist solve timing] rank %d: %d tile steps, %.1f us per step (%s)\n", d->rank, 2 * T, 1e3 * ms / (2 * T),
+                px ? "peer exchange" : "ncclAllReduce / local copies");
+        cudaEventDestroy(tev[0]); cudaEventDestroy(tev[1]);
     }
-    for (size_t i = 0; i < d->ranks.size(); ++i) {  // the bulk stream's work belongs to this solve (and joins a capture)
+    for (size_t i = 0; i < d->ranks.size(); ++i) {  // the other streams' work belongs to this solve (and joins a capture)
         DRank& r = d->ranks[i];
+        if (gs_of(r) != cs_of(r)) {
+            CK(cudaEventRecord(r.ev_swp[RING - 1], gs_of(r)));
+            CK(cudaStreamWaitEvent(cs_of(r), r.ev_swp[RING - 1], 0));
+        }
         if (!far_any[i]) continue;
         CK(cudaEventRecord(r.ev_bulk, r.bulk));
         CK(cudaStreamWaitEvent(cs_of(r), r.ev_bulk, 0));
@@ -930,14 +974,79 @@ static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CK(cudaStreamCreateWithPriority(&r.hi, cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithPriority(&r.hi2, cudaStreamNonBlocking, hi));
         }
         cudaEvent_t* evs[] = {&r.ev_tmp, &r.ev_chain, &r.ev_bulk, &r.ev_e1, &r.ev_d, &r.ev_panel[0], &r.ev_panel[1]};
         for (auto e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (int i = 0; i < DRank::kSolveRing; ++i) {
             CK(cudaEventCreateWithFlags(&r.ev_sol[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&r.ev_far[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&r.ev_swp[i], cudaEventDisableTiming));
         }
     }
+    return 0;
+}
+
+// Peer exchange set-up (collective over the world communicator): every rank allocates its exchange buffer, the CUDA IPC handles
+// travel through one byte-wise all-reduce, every rank maps every peer's buffer.  Any failure on any rank is agreed on with a
+// second all-reduce and leaves all ranks on ncclAllReduce.  Opt-in (MPLU_DIST_PEER_EXCHANGE=1, the same on every rank).
+static void px_teardown(mplu_dist* d) {
+    for (void* p : d->px_opened) cudaIpcCloseMemHandle(p);
+    d->px_opened.clear();
+    cudaFree(d->px_peers); d->px_peers = nullptr;
+    cudaFree(d->px_mine); d->px_mine = nullptr;
+    d->px_on = false;
+}
+
+static int px_setup(mplu_dist* d) {
+    const char* env = getenv("MPLU_DIST_PEER_EXCHANGE");
+    const int nr = d->nranks;
+    cudaStream_t st = d->ranks[0].chain;
+    int fail = (env && env[0] == '1') ? 0 : 1;  // opt-in: measured 69 us per tile step against 64 with ncclAllReduce (2 GPUs)
+    const size_t bytes = (kPxFlagWords + kPxDataFloats) * sizeof(float);
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (!fail && cudaMalloc(&d->px_mine, bytes) != cudaSuccess) fail = 1;
+    if (!fail && cudaMemset(d->px_mine, 0, kPxFlagWords * sizeof(unsigned)) != cudaSuccess) fail = 1;
+    if (!fail && cudaIpcGetMemHandle(&h, d->px_mine) != cudaSuccess) fail = 1;
+    cudaGetLastError();
+    // table: nr handles + one int of failure votes
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    unsigned char* dtab = nullptr;
+    CK(cudaMalloc(&dtab, nr * hb + 2 * sizeof(int)));
+    CK(cudaMemsetAsync(dtab, 0, nr * hb + 2 * sizeof(int), st));
+    int* dvote = reinterpret_cast<int*>(dtab + nr * hb);
+    auto agree = [&](int mine, int slot, int* total) -> int {  // sum of the ranks' votes
+        CK(cudaMemcpyAsync(dvote + slot, &mine, sizeof(int), cudaMemcpyHostToDevice, st));
+        NK(d->nccl->AllReduce(dvote + slot, dvote + slot, 1, ncclInt32, ncclSum, d->world, st));
+        CK(cudaMemcpyAsync(total, dvote + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    };
+    if (!fail) CK(cudaMemcpyAsync(dtab + d->rank * hb, &h, hb, cudaMemcpyHostToDevice, st));
+    NK(d->nccl->AllReduce(dtab, dtab, nr * hb, ncclUint8, ncclSum, d->world, st));
+    int total = 0;
+    int rc = agree(fail, 0, &total);
+    if (rc) { cudaFree(dtab); px_teardown(d); return rc; }
+    std::vector<float*> peers((size_t)nr, nullptr);
+    if (total == 0) {
+        std::vector<cudaIpcMemHandle_t> hs((size_t)nr);
+        CK(cudaMemcpy(hs.data(), dtab, nr * hb, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nr && !fail; ++i) {
+            if (i == d->rank) { peers[i] = d->px_mine; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hs[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { fail = 1; cudaGetLastError(); break; }
+            d->px_opened.push_back(ptr);
+            peers[i] = static_cast<float*>(ptr);
+        }
+        if (!fail && cudaMalloc(&d->px_peers, nr * sizeof(float*)) != cudaSuccess) fail = 1;
+        if (!fail && cudaMemcpy(d->px_peers, peers.data(), nr * sizeof(float*), cudaMemcpyHostToDevice) != cudaSuccess) fail = 1;
+        rc = agree(fail, 1, &total);
+        if (rc) { cudaFree(dtab); px_teardown(d); return rc; }
+    }
+    cudaFree(dtab);
+    if (total == 0) d->px_on = true;
+    else px_teardown(d);
     return 0;
 }
 
@@ -968,6 +1077,8 @@ int mplu_dist_create(mplu_dist** out, int device, int rank, int nranks, int P, i
     };
     const int rc2 = comms();
     if (rc || rc2) { mplu_dist_destroy(d); return rc ? rc : rc2; }
+    const int rc3 = px_setup(d);
+    if (rc3) { mplu_dist_destroy(d); return rc3; }
     *out = d;
     return 0;
 }
@@ -997,6 +1108,7 @@ void mplu_dist_destroy(mplu_dist* d) {
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
     if (d->solve_exec) { cudaGraphExecDestroy(d->solve_exec); d->solve_exec = nullptr; }
+    px_teardown(d);
     for (auto& r : d->ranks) {
         free_rank_work(r);
         cudaEvent_t evs[] = {r.ev_tmp, r.ev_chain, r.ev_bulk, r.ev_e1, r.ev_d, r.ev_panel[0], r.ev_panel[1]};
@@ -1004,8 +1116,10 @@ void mplu_dist_destroy(mplu_dist* d) {
         for (int i = 0; i < DRank::kSolveRing; ++i) {
             if (r.ev_sol[i]) cudaEventDestroy(r.ev_sol[i]);
             if (r.ev_far[i]) cudaEventDestroy(r.ev_far[i]);
+            if (r.ev_swp[i]) cudaEventDestroy(r.ev_swp[i]);
         }
         if (r.hi) cudaStreamDestroy(r.hi);
+        if (r.hi2) cudaStreamDestroy(r.hi2);
         mplu_destroy(r.ctx);
         mplu_destroy(r.dctx);
     }

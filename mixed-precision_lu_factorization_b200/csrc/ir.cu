@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TSV_THREADS)
 lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
                 const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
                 double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end,
-                int use_mbox, const float* __restrict__ sub) {
+                int use_mbox, const float* __restrict__ sub, const SweepPx px) {
     __shared__ __align__(16) float s_part[8][DBS];
     __shared__ __align__(16) float s_acc[DBS];
     __shared__ __align__(16) float mbox[2][TSV_MB][DBS];  // [owned-step parity][distance-1]: blocks of steps s-1 .. s-TSV_MB
@@ -266,6 +266,16 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
                         if (a == a || seen >= (unsigned)nblk) break;
                         if ((spin & 63) == 63) seen = ld_acquire_u32(ready);
                     }
+                }
+                if (px.base) {  // ... or what the peers' tile columns contributed: wait for their Q slots, add them up
+                    const unsigned* f = reinterpret_cast<const unsigned*>(px.base) + px.slot0;
+                    const long long t0 = clock64();  // a peer that never arrives must not hang the GPU (the solve then fails to converge)
+                    for (int q = 0; q < px.Q; ++q) {
+                        unsigned v;
+                        do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + q) : "memory"); }
+                        while (v != px.epoch && clock64() - t0 < 4000000000LL);
+                    }
+                    for (int q = 0; q < px.Q; ++q) sub_pre += __ldcv(px.base + kPxFlagWords + (px.slot0 + q) * px.nb + row);
                 }
                 a -= sub_pre;
 #pragma unroll
@@ -383,12 +393,12 @@ __global__ void sweep_prep_kernel(unsigned* ready, unsigned v, float* y_fill, fl
 
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st) {
-    return launch_lu_sweep(W, ldw, n, npad, Linv32, Uinv32, rhs, y, y + npad, d_out, x_accum, ready, 0, st, nullptr);
+    return launch_lu_sweep(W, ldw, n, npad, Linv32, Uinv32, rhs, y, y + npad, d_out, x_accum, ready, 0, st, nullptr, 0, nullptr);
 }
 
 int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
-                    int mode, cudaStream_t st, const float* sub, int flags) {
+                    int mode, cudaStream_t st, const float* sub, int flags, const SweepPx* px) {
     // the dynamic shared-memory opt-in and the co-residency limits are PER DEVICE: cached per device ordinal
     constexpr int kMaxDev = 64;
     static int s_max_grid[kMaxDev] = {}, s_max_grid_cl[kMaxDev] = {};
@@ -436,6 +446,7 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         g -= g % CL;
         if (g >= CL) { grid = g; use_mbox = 1; }
     }
+    const SweepPx pxv = px ? *px : SweepPx{nullptr, 0, 0, 0, 0};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(TSV_THREADS);
@@ -456,7 +467,7 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         cfg.numAttrs = use_mbox ? 1 : 0;
     }
     cudaError_t le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out,
-                                        x_accum, ready, s_begin, s_end, use_mbox, sub);
+                                        x_accum, ready, s_begin, s_end, use_mbox, sub, pxv);
     if (le != cudaSuccess && use_mbox) {  // cooperative cluster launch not available: plain cooperative launch from now on
         cudaGetLastError();
         max_grid_cl = 0;
@@ -466,7 +477,7 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         attrs[0].val.cooperative = 1;
         cfg.numAttrs = 1;
         le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out, x_accum, ready,
-                                s_begin, s_end, use_mbox, sub);
+                                s_begin, s_end, use_mbox, sub, pxv);
     }
     return (int)le;
 }

@@ -54,12 +54,23 @@ int launch_residual(const double* A, long long lda, int n, const double* x, cons
 int launch_lu_solve(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* y, double* d_out, double* x_accum, unsigned* ready, cudaStream_t st);
 
+// Partial sums that arrive from peer GPUs (block-cyclic solver, csrc/dist.cu): `base` = this rank's exchange buffer (kPxFlagWords
+// flag words, then slots of nb floats); the sweep waits until the Q flags slot0 .. slot0+Q-1 hold `epoch` and subtracts the sum
+// of those slots from its right-hand side.  The launch is already resident (its tile loads under way) when the data lands.
+constexpr unsigned long long kPxFlagWords = 16384;
+struct SweepPx {
+    const float* base;
+    unsigned long long slot0;
+    int Q, nb;
+    unsigned epoch;
+};
+
 // One sweep only: mode 0 = both (as launch_lu_solve), 1 = forward (L y = rhs, y -> ysol), 2 = backward (U x = ysol,
 // x -> xsol); used tile by tile by the block-cyclic solver.  sub (fp32, npad entries, may be null) is subtracted from the
 // right-hand side: what the other tile columns already contributed.
 int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float* Linv32, const float* Uinv32,
                     const double* rhs, float* ysol, float* xsol, double* d_out, double* x_accum, unsigned* ready,
-                    int mode, cudaStream_t st, const float* sub = nullptr, int flags = 0);
+                    int mode, cudaStream_t st, const float* sub = nullptr, int flags = 0, const struct SweepPx* px = nullptr);
 // flags: SWEEP_PREPARED = the caller has set *ready to the first step (0 forward / npad/128 backward) and filled what the sweep
 // produces with NaN (consumers poll the data); SWEEP_PLAIN_LAUNCH = small one-sweep launches without the cooperative attribute
 enum { SWEEP_PREPARED = 1, SWEEP_PLAIN_LAUNCH = 2 };
