@@ -89,6 +89,8 @@ T = n // nb
 A = orc.counter_matrix(n, seed=3)
 mine = m.scatter_block_cyclic(A, nb, P, Q)[rank].copy()
 def lt(k, PP, pp): return (k - pp) // PP + 1 if k >= pp else 0     # local tiles with global index <= k
+def ltx(k, PP, pp): return (k - 1 - pp) // PP + 1 if k > pp else 0  # ... < k
+Dtiles = []
 for k in range(T):
     pk, qk = k % P, k % Q
     D = torch.zeros(nb, nb, dtype=torch.float64)
@@ -101,6 +103,7 @@ for k in range(T):
         D = torch.tensor(t)
     dist.broadcast(D, pk * Q + qk)
     D = D.numpy()
+    Dtiles.append(D.copy())
     Lt, Ut = np.tril(D, -1) + np.eye(nb), np.triu(D)
     ilo, jlo = lt(k, P, p) * nb, lt(k, Q, q) * nb
     Lp = torch.zeros(mine.shape[0] - ilo, nb, dtype=torch.float64)
@@ -136,6 +139,38 @@ if ref is None:
         ref[j + 1:, j] /= ref[j, j]
         ref[j + 1:, j + 1:] -= np.outer(ref[j + 1:, j], ref[j, j + 1:])
 assert np.abs(LU - ref).max() <= 1e-9 * np.abs(ref).max(), np.abs(LU - ref).max()
+# 2b. the block-cyclic triangular solves as csrc/dist.cu (solve_body) runs them: right-looking with look-ahead.  Once the
+#     solution block of tile column k is known, the ranks of process column k mod Q add W_loc(:, tile column k) * block into
+#     full-length partial sums -- the next D tile rows ("near", on the chain) and every tile row beyond ("far", off the chain) --
+#     and a step is one all-reduce of the tile row's slice (ranks outside its process row hold zeros) + the replicated
+#     diagonal tile's solve.  Same ownership / range arithmetic (cnt_le, cnt_lt), checked against a dense solve.
+rhs = A @ np.arange(1.0, n + 1.0)
+mt = m.tiles_local(T, P, p)
+for D_ in (1, 2, 3):
+    y = np.zeros(n); x = np.zeros(n)
+    for sweep in (0, 1):
+        part = np.zeros(n)
+        sol = y if sweep == 0 else x
+        for kk in range(T):
+            k = kk if sweep == 0 else T - 1 - kk
+            sl = slice(k * nb, (k + 1) * nb)
+            red = torch.tensor(part[sl].copy())
+            if kk > 0: dist.all_reduce(red)
+            Dk = Dtiles[k]
+            if sweep == 0: sol[sl] = np.linalg.solve(np.tril(Dk, -1) + np.eye(nb), rhs[sl] - red.numpy())
+            else: sol[sl] = np.linalg.solve(np.triu(Dk), y[sl] - red.numpy())
+            if kk == T - 1 or q != k % Q or mine.size == 0: continue
+            if sweep == 0:
+                near0, near1 = lt(k, P, p), lt(min(k + D_, T - 1), P, p); far0, far1 = near1, mt
+            else:
+                near0, near1 = ltx(max(k - D_, 0), P, p), ltx(k, P, p); far0, far1 = 0, near0
+            c0 = (k // Q) * nb
+            for t0, t1 in ((near0, near1), (far0, far1)):
+                for tl in range(t0, t1):
+                    g = tl * P + p  # global tile row of local tile row tl
+                    assert (g > k if sweep == 0 else g < k)
+                    part[g * nb:(g + 1) * nb] += mine[tl * nb:(tl + 1) * nb, c0:c0 + nb] @ sol[sl]
+    assert np.abs(x - np.arange(1.0, n + 1.0)).max() < 1e-8, (D_, np.abs(x - np.arange(1.0, n + 1.0)).max())
 # 3. max-over-ranks timing reduction used by bench.py
 t = torch.tensor([float(rank + 1)], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)

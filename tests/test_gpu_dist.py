@@ -97,14 +97,18 @@ def test_dist_argument_errors(mplu):
         ds.close()
 
 
-def test_nccl_two_ranks(mplu):
+@pytest.mark.parametrize("peer_exchange", ["0", "1"])
+def test_nccl_two_ranks(mplu, peer_exchange):
+    """Two processes over NCCL.  peer_exchange = 1: the partial sums of the triangular solves travel through CUDA-IPC-mapped
+    peer memory (px_send_kernel, the tile sweep waits for the slots itself) instead of ncclAllReduce: same iterations."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "dist_nccl.py"), "4096", "512", "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1", MPLU_DIST_PEER_EXCHANGE=peer_exchange))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DIST")][0]
     assert "conv 1" in line and "iters 2" in line
