@@ -403,7 +403,9 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
     constexpr int kMaxDev = 64;
     static int s_max_grid[kMaxDev] = {}, s_max_grid_cl[kMaxDev] = {};
     static std::mutex s_mu;
-    constexpr int CL = 8;
+    // CTAs per cluster (mailbox hand-offs stay inside a cluster): 8; MPLU_TSV_CLUSTER = 2 / 4 for experiments (more co-resident
+    // CTAs -- 8-CTA clusters fill 120 of the 148 SMs -- against more hand-offs that cross a cluster boundary through L2)
+    static const int CL = [] { const char* e = getenv("MPLU_TSV_CLUSTER"); const int v = e ? atoi(e) : 8; return (v == 2 || v == 4) ? v : 8; }();
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDev) return (int)cudaErrorInvalidDevice;
