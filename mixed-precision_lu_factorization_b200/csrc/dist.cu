@@ -198,10 +198,20 @@ __global__ void residual_full_kernel(const double* __restrict__ b, const double*
 // partial sums meet in shared memory and one warp adds them to `part` atomically (several columns' kernels may be adding to
 // the same rows from two streams).
 __global__ void __launch_bounds__(256)
-tile_col_gemv_kernel(const float* __restrict__ W, long long ldw, int r0, int r1, int c0, const float* __restrict__ v,
-                     float* part, int nb, int P, int p) {
+tile_col_gemv_kernel(const float* __restrict__ W, long long ldw, int r0, int r1, int c0, const float* v,
+                     float* part, int nb, int P, int p, const unsigned* wait_flag, unsigned wait_val, unsigned* dbg) {
     __shared__ float4 red[8][32];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wait_flag) {  // launched ahead of its operand (tile chain): the solution block is complete when the tile sweep's step
+        if (threadIdx.x == 0) {  // counter has reached its final value
+            unsigned f;
+            const long long t0 = clock64();  // (never hang the GPU: give up after ~2 s, the solve then fails to converge)
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(wait_flag) : "memory"); }
+            while (f != wait_val && clock64() - t0 < 4000000000LL);
+            if (f != wait_val && dbg) atomicOr(dbg, 2u);
+        }
+        __syncthreads();
+    }
     const int cb = blockIdx.y * 128 + 16 * w;
     const int r = r0 + 128 * blockIdx.x + 4 * lane;  // r0, r1 are multiples of nb (a multiple of 128): no ragged block
     const float4* wp = reinterpret_cast<const float4*>(W + r + (long long)(c0 + cb) * ldw);
@@ -212,7 +222,7 @@ tile_col_gemv_kernel(const float* __restrict__ W, long long ldw, int r0, int r1,
     float x[16];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(v + cb) + u);
+        const float4 xv = __ldcg(reinterpret_cast<const float4*>(v + cb) + u);
         x[4 * u] = xv.x; x[4 * u + 1] = xv.y; x[4 * u + 2] = xv.z; x[4 * u + 3] = xv.w;
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -342,6 +352,9 @@ struct mplu_dist {
     std::vector<void*> px_opened;
     float** px_peers = nullptr;
     unsigned px_epoch = 0;
+    unsigned* px_dbg = nullptr;  // device word: bit 0 / 1 = a tile-chain / GEMV wait timed out (development)
+    unsigned* px_started_h = nullptr;  // pinned, mapped: CTAs of the tile chain that are resident
+    unsigned* px_started_d = nullptr;
 };
 
 namespace {
@@ -816,9 +829,14 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
     // peer memory (px_send_kernel -> the sweep's own wait).  With the peer exchange the sweeps have the stream cs to
     // themselves: sweep k+1 is launched behind sweep k, is resident (tile loads under way) and polling its slots while the
     // GEMVs and sends of step k run on the stream gs.
-    const bool px = d->px_on && !d->local_mode && d->ranks.size() == 1 && !d->solve_exec && env_hi && 2 * (size_t)T * Q <= kPxFlagWords &&
+    const bool px = d->px_on && d->ranks.size() == 1 && !d->solve_exec && env_hi && 2 * (size_t)T * Q <= kPxFlagWords &&
                     2 * (size_t)T * Q * nb <= kPxDataFloats;
     if (px) ++d->px_epoch;
+    // MPLU_DIST_TILE_CHAIN=1 (with the peer exchange): ALL tile sweeps of the solve are one persistent launch on cs
+    // (launch_tile_chain): nb/128 CTAs that stay resident, poll the exchange slots of the next tile row and count their steps
+    // in r.ready; the GEMVs run on gs / bulk, launched ahead, and wait for those counters on the device.
+    static const int env_chain = [] { const char* e = getenv("MPLU_DIST_TILE_CHAIN"); return e ? atoi(e) : 0; }();
+    const bool chain = px && env_chain && nb / kDiagBlock <= 64;
     auto gs_of = [&](DRank& r) { return px ? r.hi2 : cs_of(r); };
     std::vector<char> far_on(d->ranks.size() * RING, 0), far_any(d->ranks.size(), 0);
     const int sweep_flags = SWEEP_PREPARED | (env_plain ? SWEEP_PLAIN_LAUNCH : 0);
@@ -832,6 +850,7 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
         if (gs_of(r) != cs_of(r)) {
             CK(cudaEventRecord(r.ev_swp[RING - 1], cs_of(r)));
             CK(cudaStreamWaitEvent(gs_of(r), r.ev_swp[RING - 1], 0));
+            if (chain) CK(cudaStreamWaitEvent(r.bulk, r.ev_swp[RING - 1], 0));  // (its GEMVs wait on the device, not for events)
         }
     }
     // MPLU_DIST_SOLVE_TIMING=1 (development): the first hosted rank's average time per tile step of its first eager solves
@@ -842,6 +861,22 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
     if (timing) {
         CK(cudaEventCreate(&tev[0])); CK(cudaEventCreate(&tev[1]));
         CK(cudaEventRecord(tev[0], cs_of(d->ranks[0])));
+    }
+    if (chain) {  // every tile sweep of this solve: one persistent launch on cs
+        DRank& r = d->ranks[0];
+        if (!d->px_started_h && cudaHostAlloc(&d->px_started_h, sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess)
+            cudaHostGetDevicePointer(&d->px_started_d, d->px_started_h, 0);
+        cudaGetLastError();
+        const TileChain tc{2 * T, T, nb, r.Dw, r.Dl32, r.Du32, rhs[0], r.yv, r.xv, r.ready, d->px_mine, Q, d->px_epoch, d->px_dbg, d->px_started_d};
+        if (d->px_started_h) *(volatile unsigned*)d->px_started_h = 0;
+        CKI(launch_tile_chain(tc, cs_of(r)));
+        d->kernel_launches++;
+        // The GEMVs below wait for this launch ON THE DEVICE: were thousands of their blocks resident first, its CTAs (most of
+        // an SM each) would find no room and everybody would wait.  Once per solve the host waits until all of them run.
+        if (d->px_started_d) {
+            const unsigned want = (unsigned)(nb / kDiagBlock);
+            for (long long spin = 0; *(volatile unsigned*)d->px_started_h < want && spin < 2000000000LL; ++spin) {}
+        }
     }
     for (int sweep = 0; sweep < 2; ++sweep) {
         for (int kk = 0; kk < T; ++kk) {
@@ -861,7 +896,7 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
             } else if (kk > 0) {
                 CKI(allreduce(d, 0, (size_t)nb, [&](DRank& r) { return (void*)(r.part + off); }, cs_of));
             }
-            for (size_t i = 0; i < d->ranks.size(); ++i) {
+            for (size_t i = 0; i < d->ranks.size() && !chain; ++i) {
                 DRank& r = d->ranks[i];
                 const float* Dk = r.Dw + (size_t)k * nb * nb;
                 const float* Li = r.Dl32 + (size_t)k * nb * kDiagBlock;
@@ -899,17 +934,22 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
                 const float* v = (sweep == 0 ? r.yv : r.xv) + (size_t)k * nb;
                 float* part = r.part + (size_t)sweep * n;
                 const int c0 = (k / Q) * nb;
+                // with the tile chain the GEMVs are launched ahead and wait for tile sweep (sweep, k) on the device
+                const unsigned* wf = chain ? r.ready + (size_t)sweep * T + k : nullptr;
+                const unsigned wv = (unsigned)((sweep + 1) * (nb / kDiagBlock));
                 auto gemv = [&](int t0, int t1, cudaStream_t st) {
                     const int r0 = t0 * nb, r1 = t1 * nb;
                     dim3 grid((unsigned)((r1 - r0) / 128), (unsigned)(nb / 128));
-                    tile_col_gemv_kernel<<<grid, 256, 0, st>>>(r.W, r.mloc, r0, r1, c0, v, part, nb, P, r.p);
+                    tile_col_gemv_kernel<<<grid, 256, 0, st>>>(r.W, r.mloc, r0, r1, c0, v, part, nb, P, r.p, wf, wv, d->px_dbg);
                     d->kernel_launches++;
                 };
                 if (near1 > near0) gemv(near0, near1, gs_of(r));
                 if (far1 > far0 && !env_far) gemv(far0, far1, gs_of(r));  // experiment: everything in stream order
                 else if (far1 > far0) {
-                    CK(cudaEventRecord(r.ev_sol[kk % RING], gs_of(r)));
-                    CK(cudaStreamWaitEvent(r.bulk, r.ev_sol[kk % RING], 0));
+                    if (!chain) {
+                        CK(cudaEventRecord(r.ev_sol[kk % RING], gs_of(r)));
+                        CK(cudaStreamWaitEvent(r.bulk, r.ev_sol[kk % RING], 0));
+                    }
                     gemv(far0, far1, r.bulk);
                     CK(cudaEventRecord(r.ev_far[kk % RING], r.bulk));
                     far_on[i * RING + kk % RING] = 1;
@@ -924,8 +964,10 @@ int solve_body(mplu_dist* d, const std::vector<const double*>& rhs) {
         CK(cudaEventSynchronize(tev[1]));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, tev[0], tev[1]);
-        fprintf(stderr, "[mplu dist solve timing] rank %d: %d tile steps, %.1f us per step (%s)\n", d->rank, 2 * T, 1e3 * ms / (2 * T),
-                px ? "peer exchange" : "ncclAllReduce / local copies");
+        unsigned dbg = 0;
+        if (d->px_dbg) cudaMemcpy(&dbg, d->px_dbg, sizeof(dbg), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[mplu dist solve timing] rank %d: %d tile steps, %.1f us per step (%s%s), timed-out waits 0x%x\n", d->rank, 2 * T,
+                1e3 * ms / (2 * T), px ? "peer exchange" : "ncclAllReduce / local copies", chain ? ", tile chain" : "", dbg);
         cudaEventDestroy(tev[0]); cudaEventDestroy(tev[1]);
     }
     for (size_t i = 0; i < d->ranks.size(); ++i) {  // the other streams' work belongs to this solve (and joins a capture)
@@ -965,6 +1007,13 @@ static int dist_create_common(mplu_dist* d, int device, int P, int Q) {
     CK(cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device));
     mplu_default_options(&d->opts);
     CK(cudaEventCreate(&d->ev0)); CK(cudaEventCreate(&d->ev1)); CK(cudaEventCreate(&d->ev2));
+    {   // The tile chain (MPLU_DIST_TILE_CHAIN) is a kernel that stays resident and WAITS for these two: with CUDA's lazy
+        // module loading the first launch of a kernel may have to wait for running kernels to finish, i.e. for the chain's
+        // time-outs (found the hard way: every wait of the first solve ran into its 2 s limit).  Load them now.
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, px_send_kernel));
+        CK(cudaFuncGetAttributes(&fa, tile_col_gemv_kernel));
+    }
     for (auto& r : d->ranks) {
         CKI(mplu_create(&r.ctx, device));
         CKI(mplu_create(&r.dctx, device));
@@ -995,6 +1044,9 @@ static void px_teardown(mplu_dist* d) {
     d->px_opened.clear();
     cudaFree(d->px_peers); d->px_peers = nullptr;
     cudaFree(d->px_mine); d->px_mine = nullptr;
+    cudaFree(d->px_dbg); d->px_dbg = nullptr;
+    if (d->px_started_h) cudaFreeHost(d->px_started_h);
+    d->px_started_h = d->px_started_d = nullptr;
     d->px_on = false;
 }
 
@@ -1009,6 +1061,7 @@ static int px_setup(mplu_dist* d) {
     if (!fail && cudaMalloc(&d->px_mine, bytes) != cudaSuccess) fail = 1;
     if (!fail && cudaMemset(d->px_mine, 0, kPxFlagWords * sizeof(unsigned)) != cudaSuccess) fail = 1;
     if (!fail && cudaIpcGetMemHandle(&h, d->px_mine) != cudaSuccess) fail = 1;
+    if (!fail && (cudaMalloc(&d->px_dbg, sizeof(unsigned)) != cudaSuccess || cudaMemset(d->px_dbg, 0, sizeof(unsigned)) != cudaSuccess)) fail = 1;
     cudaGetLastError();
     // table: nr handles + one int of failure votes
     const size_t hb = sizeof(cudaIpcMemHandle_t);
@@ -1097,6 +1150,18 @@ int mplu_dist_create_local(mplu_dist** out, int device, int P, int Q) {
         }
     const int rc = dist_create_common(d, device, P, Q);
     if (rc) { mplu_dist_destroy(d); return rc; }
+    {   // a single hosted rank can run the peer-exchange code path against its own buffer (one-GPU testing of that path)
+        const char* env = getenv("MPLU_DIST_PEER_EXCHANGE");
+        if (env && env[0] == '1' && P * Q == 1) {
+            const size_t bytes = (kPxFlagWords + kPxDataFloats) * sizeof(float);
+            bool ok = cudaMalloc(&d->px_mine, bytes) == cudaSuccess && cudaMemset(d->px_mine, 0, kPxFlagWords * sizeof(unsigned)) == cudaSuccess &&
+                      cudaMalloc(&d->px_peers, sizeof(float*)) == cudaSuccess &&
+                      cudaMemcpy(d->px_peers, &d->px_mine, sizeof(float*), cudaMemcpyHostToDevice) == cudaSuccess &&
+                      cudaMalloc(&d->px_dbg, sizeof(unsigned)) == cudaSuccess && cudaMemset(d->px_dbg, 0, sizeof(unsigned)) == cudaSuccess;
+            if (ok) d->px_on = true;
+            else px_teardown(d);
+        }
+    }
     *out = d;
     return 0;
 }

@@ -158,10 +158,10 @@ __device__ __forceinline__ void st_relaxed_f1(float* p, float v) {
 }
 
 __global__ void __launch_bounds__(TSV_THREADS)
-lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, const float* __restrict__ Linv,
-                const float* __restrict__ Uinv, const double* __restrict__ rhs, float* ysol, float* xsol,
-                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready, int s_begin, int s_end,
-                int use_mbox, const float* __restrict__ sub, const SweepPx px) {
+lu_solve_kernel(const float* __restrict__ W_, long long ldw, int n, int nblk, const float* __restrict__ Linv_,
+                const float* __restrict__ Uinv_, const double* __restrict__ rhs_, float* ysol_, float* xsol_,
+                double* __restrict__ d_out, double* __restrict__ x_accum, unsigned* ready_, int s_begin_, int s_end_,
+                int use_mbox, const float* __restrict__ sub, const SweepPx px_, const TileChain tc) {
     __shared__ __align__(16) float s_part[8][DBS];
     __shared__ __align__(16) float s_acc[DBS];
     __shared__ __align__(16) float mbox[2][TSV_MB][DBS];  // [owned-step parity][distance-1]: blocks of steps s-1 .. s-TSV_MB
@@ -175,7 +175,31 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
         for (int e = tid; e < 2 * TSV_MB * DBS; e += TSV_THREADS) (&mbox[0][0][0])[e] = __int_as_float(0x7fffffff);
         ptx::cluster_sync_all();  // nobody stores into a mailbox that is not initialised yet
     }
+    if (tc.count > 0 && tc.started && tid == 0) atomicAdd_system(tc.started, 1u);
     int kown = 0;
+    // tc.count > 0: a chain of one-sweep problems (the diagonal tiles of a block-cyclic solve) in this one launch
+    const int nprob = tc.count > 0 ? tc.count : 1;
+    for (int ts = 0; ts < nprob; ++ts) {
+    const float* W = W_; const float* Linv = Linv_; const float* Uinv = Uinv_; const double* rhs = rhs_;
+    float* ysol = ysol_; float* xsol = xsol_; unsigned* ready = ready_;
+    int s_begin = s_begin_, s_end = s_end_;
+    SweepPx px = px_;
+    if (tc.count > 0) {
+        const int swp = ts / tc.T, kk = ts - swp * tc.T, k = swp == 0 ? kk : tc.T - 1 - kk;
+        W = tc.Dw + (size_t)k * tc.nb * tc.nb;
+        Linv = tc.Dl32 + (size_t)k * tc.nb * DBS;
+        Uinv = tc.Du32 + (size_t)k * tc.nb * DBS;
+        rhs = tc.rhs + (size_t)k * tc.nb;
+        ysol = tc.yv + (size_t)k * tc.nb;
+        xsol = tc.xv + (size_t)k * tc.nb;
+        ready = tc.ready + (size_t)swp * tc.T + k;
+        s_begin = swp == 0 ? 0 : nblk;
+        s_end = swp == 0 ? nblk : 2 * nblk;
+        px.base = kk > 0 ? tc.px_base : nullptr;
+        px.slot0 = ((unsigned long long)swp * tc.T + k) * tc.Q;
+        px.Q = tc.Q; px.nb = tc.nb; px.epoch = tc.epoch;
+        seen = 0;
+    }
     // steps [s_begin, s_end): [0, 2*nblk) = both sweeps; [0, nblk) forward only; [nblk, 2*nblk) backward only (its
     // right-hand side is then read from ysol and *ready must start at nblk)
     for (int s = s_begin + blockIdx.x; s < s_end; s += gridDim.x, ++kown) {
@@ -275,6 +299,7 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
                         do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + q) : "memory"); }
                         while (v != px.epoch && clock64() - t0 < 4000000000LL);
                     }
+                    if (tc.dbg && clock64() - t0 >= 4000000000LL) atomicOr(tc.dbg, 1u);
                     for (int q = 0; q < px.Q; ++q) sub_pre += __ldcv(px.base + kPxFlagWords + (px.slot0 + q) * px.nb + row);
                 }
                 a -= sub_pre;
@@ -357,6 +382,7 @@ lu_solve_kernel(const float* __restrict__ W, long long ldw, int n, int nblk, con
             st_release_u32(ready, (unsigned)(s + 1));
         }
     }
+    }  // ts
     if (use_mbox) ptx::cluster_sync_all();  // no CTA leaves while a neighbour may still store into its mailbox
 }
 
@@ -469,7 +495,7 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         cfg.numAttrs = use_mbox ? 1 : 0;
     }
     cudaError_t le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out,
-                                        x_accum, ready, s_begin, s_end, use_mbox, sub, pxv);
+                                        x_accum, ready, s_begin, s_end, use_mbox, sub, pxv, TileChain{});
     if (le != cudaSuccess && use_mbox) {  // cooperative cluster launch not available: plain cooperative launch from now on
         cudaGetLastError();
         max_grid_cl = 0;
@@ -479,9 +505,32 @@ int launch_lu_sweep(const float* W, long long ldw, int n, int npad, const float*
         attrs[0].val.cooperative = 1;
         cfg.numAttrs = 1;
         le = cudaLaunchKernelEx(&cfg, lu_solve_kernel, W, ldw, n, nblk, Linv32, Uinv32, rhs, ysol, xsol, d_out, x_accum, ready,
-                                s_begin, s_end, use_mbox, sub, pxv);
+                                s_begin, s_end, use_mbox, sub, pxv, TileChain{});
     }
     return (int)le;
+}
+
+// every tile sweep of a block-cyclic solve in one launch: nb/128 CTAs (one step of each tile sweep per CTA) in clusters of 8,
+// resident for the whole solve; see TileChain
+int launch_tile_chain(const TileChain& tc, cudaStream_t st) {
+    constexpr int CL = 8;
+    const int nblk = tc.nb / DBS;
+    if (tc.count <= 0 || nblk <= 0 || nblk > 64 || tc.nb % DBS) return (int)cudaErrorInvalidValue;
+    const int use_mbox = (nblk % CL == 0) ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nblk);
+    cfg.blockDim = dim3(TSV_THREADS);
+    cfg.dynamicSmemBytes = TSV_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CL; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = use_mbox ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, lu_solve_kernel, (const float*)nullptr, (long long)tc.nb, tc.nb, nblk, (const float*)nullptr,
+                                   (const float*)nullptr, (const double*)nullptr, (float*)nullptr, (float*)nullptr, (double*)nullptr,
+                                   (double*)nullptr, (unsigned*)nullptr, 0, 0, use_mbox, (const float*)nullptr,
+                                   SweepPx{nullptr, 0, 0, 0, 0}, tc);
 }
 
 }  // namespace mplu

@@ -65,6 +65,28 @@ struct SweepPx {
     unsigned epoch;
 };
 
+// All tile sweeps of one block-cyclic solve in ONE persistent launch (csrc/dist.cu, MPLU_DIST_TILE_CHAIN=1 with the peer
+// exchange): count = 2 T tile sweeps, forward over the replicated diagonal tiles k = 0 .. T-1, then backward k = T-1 .. 0; tile
+// sweep (sweep, k) takes its right-hand side from rhs + k nb (forward) / yv + k nb (backward) minus the partial sums that arrive
+// in the exchange slots ((sweep T + k) Q ..) -- except the first tile of each sweep, which has none --, writes yv / xv + k nb
+// and counts its steps in ready[sweep T + k] (final value nb/128 forward, 2 nb/128 backward: what the GEMV kernels of the step
+// wait for on the device).  dbg: bit 0 is set when a wait for the exchange slots timed out.
+struct TileChain {
+    int count, T, nb;
+    const float *Dw, *Dl32, *Du32;
+    const double* rhs;
+    float *yv, *xv;
+    unsigned* ready;
+    const float* px_base;
+    int Q;
+    unsigned epoch;
+    unsigned* dbg;
+    unsigned* started;  // host-visible counter (may be null): every CTA adds 1 once it is resident -- the host enqueues the
+                        // kernels that wait for this launch on the device only after all of them are, so that their
+                        // blocks cannot take its SMs first
+};
+int launch_tile_chain(const TileChain& tc, cudaStream_t st);
+
 // One sweep only: mode 0 = both (as launch_lu_solve), 1 = forward (L y = rhs, y -> ysol), 2 = backward (U x = ysol,
 // x -> xsol); used tile by tile by the block-cyclic solver.  sub (fp32, npad entries, may be null) is subtracted from the
 // right-hand side: what the other tile columns already contributed.
